@@ -1,0 +1,154 @@
+"""ctypes binding of the C ABI in include/b200dpf.h.
+
+This is the binding a non-torch host (or the reference's maintainers, see
+INTEGRATION.md) would write: plain pointers and sizes over libb200dpf.so.  The
+torch-facing module is `dpf_cpp` (csrc/dpf_cpp_ext.cpp); this one is used by the
+parity tests and the benchmark, which want to drive the ABI directly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200dpf.so")
+KEY_WORDS = 524
+PRF_DUMMY, PRF_SALSA20, PRF_CHACHA20, PRF_AES128 = 0, 1, 2, 3
+PRF_NAMES = {0: "DUMMY", 1: "SALSA20", 2: "CHACHA20", 3: "AES128"}
+
+# every symbol include/b200dpf.h declares
+SYMBOLS = [
+    "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_batch", "b200dpf_eval_cpu",
+    "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
+    "b200dpf_eval_device", "b200dpf_expand_device", "b200dpf_ctx_n", "b200dpf_ctx_entry_size",
+    "b200dpf_ctx_device", "b200dpf_ctx_last_launches", "b200dpf_ctx_set_subtree_log2",
+]
+
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+
+
+class B200DPFError(RuntimeError):
+    pass
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libb200dpf.so not built (run `python gpu-dpf_b200/build.py`); there is no fallback")
+    L = C.CDLL(LIB_PATH)
+    L.b200dpf_version.restype = C.c_char_p
+    L.b200dpf_last_error.restype = C.c_char_p
+    L.b200dpf_gen.argtypes = [C.c_int64, C.c_int64, C.c_char_p, C.c_size_t, C.c_int, _i32p, _i32p]
+    L.b200dpf_gen_batch.argtypes = [_i64p, _u32p, C.c_int64, C.c_int64, C.c_int, C.c_int, _i32p, _i32p]
+    L.b200dpf_eval_cpu.argtypes = [_i32p, C.c_int, _i32p]
+    L.b200dpf_key_n.argtypes = [_i32p]
+    L.b200dpf_key_n.restype = C.c_int64
+    L.b200dpf_key_depth.argtypes = [_i32p]
+    L.b200dpf_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.b200dpf_destroy.argtypes = [C.c_void_p]
+    L.b200dpf_eval.argtypes = [C.c_void_p, _i32p, C.c_int64, C.c_int, _i32p]
+    L.b200dpf_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    L.b200dpf_expand_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    L.b200dpf_ctx_n.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_n.restype = C.c_int64
+    L.b200dpf_ctx_entry_size.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_device.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_last_launches.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_set_subtree_log2.argtypes = [C.c_void_p, C.c_int]
+    return L
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = load()
+    return _LIB
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise B200DPFError("%s failed (%d): %s" % (what, rc, lib().b200dpf_last_error().decode()))
+
+
+def gen(alpha, n, seed32, prf):
+    a = np.zeros(KEY_WORDS, np.int32)
+    b = np.zeros(KEY_WORDS, np.int32)
+    seed = int(seed32 & 0xFFFFFFFF).to_bytes(4, "little")
+    _check(lib().b200dpf_gen(alpha, n, seed, len(seed), prf, a, b), "b200dpf_gen")
+    return a, b
+
+
+def gen_batch(alphas, n, seeds32, prf, nthreads=0):
+    alphas = np.ascontiguousarray(alphas, np.int64)
+    seeds32 = np.ascontiguousarray(np.asarray(seeds32, np.int64) & 0xFFFFFFFF, np.uint32)
+    a = np.zeros((len(alphas), KEY_WORDS), np.int32)
+    b = np.zeros((len(alphas), KEY_WORDS), np.int32)
+    _check(lib().b200dpf_gen_batch(alphas, seeds32, len(alphas), n, prf, nthreads, a, b), "b200dpf_gen_batch")
+    return a, b
+
+
+def eval_cpu(key, prf):
+    key = np.ascontiguousarray(key, np.int32)
+    n = lib().b200dpf_key_n(key)
+    if n < 0:
+        raise B200DPFError("malformed key")
+    out = np.zeros(n, np.int32)
+    _check(lib().b200dpf_eval_cpu(key, prf, out), "b200dpf_eval_cpu")
+    return out
+
+
+class Context:
+    """One table (or one entry-range shard of it) resident on one GPU."""
+
+    def __init__(self, table, device=0, shard_rank=0, shard_count=1):
+        table = np.ascontiguousarray(table, np.int32)
+        assert table.ndim == 2
+        self.n, self.entry_size = table.shape
+        self.handle = C.c_void_p()
+        _check(lib().b200dpf_create(C.byref(self.handle), table.ctypes.data_as(C.c_void_p), self.n, self.entry_size,
+                                    device, shard_rank, shard_count), "b200dpf_create")
+
+    @classmethod
+    def from_device_ptr(cls, ptr, n, entry_size, device=0, shard_rank=0, shard_count=1):
+        self = cls.__new__(cls)
+        self.n, self.entry_size = n, entry_size
+        self.handle = C.c_void_p()
+        _check(lib().b200dpf_create(C.byref(self.handle), C.c_void_p(ptr), n, entry_size, device, shard_rank,
+                                    shard_count), "b200dpf_create")
+        return self
+
+    def eval(self, keys, prf):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, KEY_WORDS)
+        out = np.zeros((keys.shape[0], self.entry_size), np.int32)
+        _check(lib().b200dpf_eval(self.handle, keys, keys.shape[0], prf, out), "b200dpf_eval")
+        return out
+
+    def eval_device(self, keys_ptr, nkeys, prf, out_ptr, stream=0):
+        _check(lib().b200dpf_eval_device(self.handle, C.c_void_p(keys_ptr), nkeys, prf, C.c_void_p(out_ptr),
+                                         C.c_void_p(stream)), "b200dpf_eval_device")
+
+    def expand_device(self, keys_ptr, nkeys, prf, out_ptr, stream=0):
+        _check(lib().b200dpf_expand_device(self.handle, C.c_void_p(keys_ptr), nkeys, prf, C.c_void_p(out_ptr),
+                                           C.c_void_p(stream)), "b200dpf_expand_device")
+
+    def set_subtree_log2(self, s):
+        _check(lib().b200dpf_ctx_set_subtree_log2(self.handle, s), "b200dpf_ctx_set_subtree_log2")
+
+    @property
+    def last_launches(self):
+        return lib().b200dpf_ctx_last_launches(self.handle)
+
+    def close(self):
+        if self.handle:
+            lib().b200dpf_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,469 @@
+/*
+ * dpf_capi.cu -- implementation of the C ABI declared in include/b200dpf.h.
+ *
+ * Owns the device state of one table (or one entry-range shard of it) and
+ * turns b200dpf_eval* calls into launches of the sm_100a kernel in
+ * dpf_kernels.cu.  The GPU entry points have no CPU fallback: without a usable
+ * CUDA device they fail with B200DPF_ECUDA.
+ */
+#include "b200dpf.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "dpf_host.h"
+#include "dpf_kernels.cuh"
+
+using namespace b200dpf;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(B200DPF_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__),       \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+int ilog2(int64_t v)
+{
+    int b = 0;
+    while (((int64_t)1 << b) < v) b++;
+    return b;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct b200dpf_ctx {
+    int device = 0;
+    int64_t n = 0;
+    int depth = 0;
+    int entry_size = 0;
+    int entry_pad = 0;       /* entry size rounded up to 16 int32 (64-byte rows) */
+    int shard_rank = 0, shard_count = 1, shard_bits = 0;
+    int64_t n_local = 0;
+    int depth_local = 0;
+    int32_t *d_table = nullptr;
+    cudaStream_t stream = nullptr;
+    int32_t *d_keys = nullptr;
+    size_t keys_cap = 0;     /* keys */
+    int32_t *d_out = nullptr;
+    size_t out_cap = 0;      /* int32 elements */
+    uint32_t *d_counters = nullptr;
+    size_t counters_cap = 0;
+    int sm_count = 0;
+    uint32_t smem_base = 0;
+    int s_override = 0;
+    int last_launches = 0;
+};
+
+namespace {
+
+struct LaunchPlan {
+    EvalParams p;
+    int grid;
+    size_t smem;
+};
+
+/* Decide subtree size, grid and the dynamic shared memory layout. */
+int plan_launch(b200dpf_ctx *c, int prf, int mode, int64_t nkeys, LaunchPlan *plan)
+{
+    EvalParams &p = plan->p;
+    std::memset(&p, 0, sizeof p);
+    const int threads = eval_threads(prf);
+    const int blocks_per_sm = eval_min_blocks(prf);
+    int max_smem = 0;
+    CUDA_TRY(eval_max_smem(prf, mode, &max_smem));
+    int sm_total = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+    /* every resident block also pays the 1 KiB system reservation */
+    int budget = std::min(max_smem, sm_total / blocks_per_sm - 1024);
+    budget &= ~15;
+
+    const uint32_t meta_cw = (uint32_t)c->depth * 4u * 32u * 16u;
+    const uint32_t meta = meta_cw + 512u + 512u + 16u;
+    const uint32_t level_bytes = (uint32_t)threads * 16u;
+
+    int s_max;
+    uint32_t off_meta, off_lo, off_hi;
+    int cap_lo, cap_hi;   /* stack levels that fit in each region */
+    if (prf == B200DPF_PRF_AES128) {
+        /* tables: 128 KiB whose shared-window address is 64 KiB aligned */
+        const uint32_t tab_abs = (c->smem_base + 65535u) & ~65535u;
+        const uint32_t off_tab = tab_abs - c->smem_base;
+        const uint32_t a_size = off_tab;                         /* region A: before the tables */
+        const uint32_t b_off = off_tab + 131072u;                /* region B: after them        */
+        if ((int64_t)budget < (int64_t)b_off) return fail(B200DPF_ECUDA, "shared memory too small for AES tables");
+        const uint32_t b_size = (uint32_t)budget - b_off;
+        p.off_tab = off_tab;
+        uint32_t a_used = 0, b_used = 0;
+        if (meta <= a_size) { off_meta = 0; a_used = meta; }
+        else if (meta <= b_size) { off_meta = b_off; b_used = meta; }
+        else return fail(B200DPF_EINVAL, "depth %d needs more shared memory than available", c->depth);
+        a_used = (a_used + 15u) & ~15u;
+        b_used = (b_used + 15u) & ~15u;
+        off_lo = b_off + b_used;
+        cap_lo = (int)((b_size - b_used) / level_bytes);
+        off_hi = a_used;
+        cap_hi = (int)((a_size - a_used) / level_bytes);
+        plan->smem = (size_t)budget;
+    } else {
+        off_meta = 0;
+        off_lo = (meta + 15u) & ~15u;
+        if ((int64_t)budget < (int64_t)off_lo) return fail(B200DPF_EINVAL, "depth %d needs more shared memory than available", c->depth);
+        cap_lo = (int)(((uint32_t)budget - off_lo) / level_bytes);
+        off_hi = off_lo;
+        cap_hi = 0;
+        plan->smem = 0;   /* set below once s is known */
+    }
+    s_max = 1 + cap_lo + cap_hi;
+
+    plan->grid = c->sm_count * blocks_per_sm;
+    const int64_t key_groups = (nkeys + 31) / 32;
+    const int64_t warps = (int64_t)plan->grid * (threads / 32);
+
+    int s = std::min(c->depth_local, std::min(s_max, 10));
+    if (c->s_override > 0) {
+        s = std::min(c->s_override, std::min(c->depth_local, s_max));
+    } else {
+        /* enough work items for every resident warp to draw several */
+        while (s > 5 && (((int64_t)1 << (c->depth_local - s)) * key_groups) < 6 * warps) s--;
+    }
+    if (s < 1) s = 1;
+
+    p.depth = c->depth;
+    p.s = s;
+    p.nsub = (uint32_t)1 << (c->depth_local - s);
+    p.sub_first = (uint32_t)c->shard_rank << (c->depth_local - s);
+    p.nkeys = (int)nkeys;
+    p.key_groups = (int)key_groups;
+    p.table = reinterpret_cast<const uint4 *>(c->d_table);
+    p.row_stride_v = (uint32_t)c->entry_pad / 4u;
+    p.out_stride = (uint32_t)c->entry_size;
+    p.n = (uint64_t)c->n;
+    p.off_cw = off_meta;
+    p.off_cwlo = off_meta + meta_cw;
+    p.off_root = p.off_cwlo + 512u;
+    p.off_flag = p.off_root + 512u;
+    p.off_stack_lo = off_lo;
+    p.off_stack_hi = off_hi;
+    p.stack_split = std::min(cap_lo, s - 1);
+    if (prf != B200DPF_PRF_AES128) plan->smem = (size_t)off_lo + (size_t)(s > 1 ? s - 1 : 0) * level_bytes;
+    if (plan->grid > (int)(key_groups * p.nsub * 1)) {
+        /* fewer work items than blocks: still fine, idle blocks exit quickly */
+    }
+    return B200DPF_OK;
+}
+
+int ensure_counters(b200dpf_ctx *c, size_t count)
+{
+    if (count <= c->counters_cap) return B200DPF_OK;
+    if (c->d_counters) cudaFree(c->d_counters);
+    c->d_counters = nullptr;
+    c->counters_cap = 0;
+    CUDA_TRY(cudaMalloc(&c->d_counters, count * sizeof(uint32_t)));
+    c->counters_cap = count;
+    return B200DPF_OK;
+}
+
+int run_eval(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *out_dev, cudaStream_t stream)
+{
+    LaunchPlan plan;
+    int rc = plan_launch(c, prf, 0, nkeys, &plan);
+    if (rc) return rc;
+    const int passes = c->entry_pad / 16;
+    rc = ensure_counters(c, (size_t)passes * (size_t)plan.p.key_groups);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, (size_t)passes * plan.p.key_groups * sizeof(uint32_t), stream));
+    CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)nkeys * c->entry_size * sizeof(int32_t), stream));
+    plan.p.keys = reinterpret_cast<const uint4 *>(keys_dev);
+    plan.p.out = reinterpret_cast<uint32_t *>(out_dev);
+    c->last_launches = 0;
+    for (int pass = 0; pass < passes; pass++) {
+        plan.p.col_off_v = (uint32_t)pass * 4u;
+        plan.p.col_off = (uint32_t)pass * 16u;
+        plan.p.ncols = (uint32_t)std::min(16, c->entry_size - pass * 16);
+        plan.p.counters = c->d_counters + (size_t)pass * plan.p.key_groups;
+        CUDA_TRY(launch_eval(prf, 0, plan.p, plan.grid, plan.smem, stream));
+        c->last_launches++;
+    }
+    return B200DPF_OK;
+}
+
+int check_eval_args(const b200dpf_ctx *c, const void *keys, int64_t nkeys, int prf, const void *out)
+{
+    if (!c) return fail(B200DPF_EINVAL, "null context");
+    if (!c->d_table) return fail(B200DPF_ESTATE, "context has no table");
+    if (!keys || !out) return fail(B200DPF_EINVAL, "null buffer");
+    if (nkeys < 1 || nkeys > (int64_t)1 << 24) return fail(B200DPF_EINVAL, "nkeys=%lld out of range", (long long)nkeys);
+    if (prf < B200DPF_PRF_DUMMY || prf > B200DPF_PRF_AES128) return fail(B200DPF_EINVAL, "unknown prf id %d", prf);
+    return B200DPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *b200dpf_version(void) { return "b200dpf 0.1.0 sm_100a"; }
+
+const char *b200dpf_last_error(void) { return g_err; }
+
+int b200dpf_gen(int64_t alpha, int64_t n, const uint8_t *seed, size_t seed_len, int prf,
+                int32_t *key_a, int32_t *key_b)
+{
+    if (!key_a || !key_b) return fail(B200DPF_EINVAL, "null key buffer");
+    uint32_t seed32 = 0;
+    for (size_t i = 0; i < 4 && i < seed_len && seed; i++) seed32 |= (uint32_t)seed[i] << (8 * i);
+    if (host::gen(alpha, n, seed32, prf, key_a, key_b) != 0)
+        return fail(B200DPF_EINVAL, "gen: need power-of-two n >= 2, 0 <= alpha < n, valid prf (alpha=%lld n=%lld prf=%d)",
+                    (long long)alpha, (long long)n, prf);
+    return B200DPF_OK;
+}
+
+int b200dpf_gen_batch(const int64_t *alphas, const uint32_t *seeds32, int64_t count, int64_t n, int prf,
+                      int nthreads, int32_t *keys_a, int32_t *keys_b)
+{
+    if (!alphas || !seeds32 || !keys_a || !keys_b || count < 0) return fail(B200DPF_EINVAL, "bad gen_batch argument");
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    nthreads = (int)std::min<int64_t>(nthreads, std::max<int64_t>(count, 1));
+    std::vector<int> rcs((size_t)nthreads, 0);
+    auto work = [&](int t) {
+        for (int64_t i = t; i < count; i += nthreads)
+            if (host::gen(alphas[i], n, seeds32[i], prf, keys_a + i * host::KEY_WORDS, keys_b + i * host::KEY_WORDS))
+                rcs[(size_t)t] = -1;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    for (int r : rcs)
+        if (r) return fail(B200DPF_EINVAL, "gen_batch: invalid alpha/n/prf in batch");
+    return B200DPF_OK;
+}
+
+int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n)
+{
+    if (!key || !out_n) return fail(B200DPF_EINVAL, "null buffer");
+    if (host::eval_cpu(key, prf, out_n) != 0) return fail(B200DPF_EINVAL, "eval_cpu: malformed key or prf id");
+    return B200DPF_OK;
+}
+
+int64_t b200dpf_key_n(const int32_t *key) { return key ? host::key_n(key) : -1; }
+int b200dpf_key_depth(const int32_t *key) { return key ? host::key_depth(key) : -1; }
+
+int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry_size, int device,
+                   int shard_rank, int shard_count)
+{
+    if (!out) return fail(B200DPF_EINVAL, "null ctx out pointer");
+    *out = nullptr;
+    if (!table) return fail(B200DPF_EINVAL, "null table");
+    if (n < 2 || n > ((int64_t)1 << 31) || (n & (n - 1)) != 0)
+        return fail(B200DPF_EINVAL, "table size n=%lld must be a power of two in [2, 2^31]", (long long)n);
+    if (entry_size < 1 || entry_size > 4096) return fail(B200DPF_EINVAL, "entry_size=%d out of range [1,4096]", entry_size);
+    if (shard_count < 1 || (shard_count & (shard_count - 1)) != 0 || (int64_t)shard_count > n / 2 ||
+        shard_rank < 0 || shard_rank >= shard_count)
+        return fail(B200DPF_EINVAL, "bad shard %d of %d for n=%lld", shard_rank, shard_count, (long long)n);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(B200DPF_ECUDA, "no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(B200DPF_EINVAL, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", device);
+
+    b200dpf_ctx *c = new (std::nothrow) b200dpf_ctx();
+    if (!c) return fail(B200DPF_ENOMEM, "out of host memory");
+    c->device = device;
+    c->n = n;
+    c->depth = ilog2(n);
+    c->entry_size = entry_size;
+    c->entry_pad = (entry_size + 15) & ~15;
+    c->shard_rank = shard_rank;
+    c->shard_count = shard_count;
+    c->shard_bits = ilog2(shard_count);
+    c->n_local = n / shard_count;
+    c->depth_local = c->depth - c->shard_bits;
+
+#define CTX_TRY(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            fail(B200DPF_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            b200dpf_destroy(c);                                                                \
+            return B200DPF_ECUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+    CTX_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CTX_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
+    CTX_TRY(upload_aes_table(host::aes_te0()));
+
+    /* Table: gather this shard's rows (natural indices j*G + bitrev_g(rank)),
+     * then permute on the device into breadth-first leaf order, padded to
+     * 64-byte rows.  dpf_wrapper.cu:103-115 does the analogous reorder on the
+     * host with one ATen call per element. */
+    const size_t row_bytes = (size_t)entry_size * sizeof(int32_t);
+    const size_t stage_bytes = (size_t)c->n_local * row_bytes;
+    const size_t table_bytes = (size_t)c->n_local * (size_t)c->entry_pad * sizeof(int32_t);
+    int32_t *d_stage = nullptr;
+    CTX_TRY(cudaMalloc(&d_stage, stage_bytes));
+    cudaError_t e = cudaSuccess;
+    if (shard_count == 1) {
+        e = cudaMemcpyAsync(d_stage, table, stage_bytes, cudaMemcpyDefault, c->stream);
+    } else {
+        uint32_t rr = 0;
+        for (int i = 0; i < c->shard_bits; i++) rr |= (((uint32_t)shard_rank >> i) & 1u) << (c->shard_bits - 1 - i);
+        const int32_t *src = table + (size_t)rr * entry_size;
+        cudaPointerAttributes attr;
+        const bool on_device = cudaPointerGetAttributes(&attr, table) == cudaSuccess &&
+                               (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (on_device) {
+            e = cudaMemcpy2DAsync(d_stage, row_bytes, src, row_bytes * shard_count, row_bytes, (size_t)c->n_local,
+                                  cudaMemcpyDefault, c->stream);
+        } else {
+            std::vector<int32_t> gathered((size_t)c->n_local * entry_size);
+            for (int64_t j = 0; j < c->n_local; j++)
+                std::memcpy(gathered.data() + (size_t)j * entry_size, src + (size_t)j * shard_count * entry_size, row_bytes);
+            e = cudaMemcpyAsync(d_stage, gathered.data(), stage_bytes, cudaMemcpyHostToDevice, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        }
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_table, table_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_table, 0, table_bytes, c->stream);
+    if (e == cudaSuccess)
+        e = launch_permute_table(d_stage, c->d_table, (uint64_t)c->n_local, c->depth_local, entry_size, c->entry_pad, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_stage);
+    CTX_TRY(e);
+#undef CTX_TRY
+    *out = c;
+    return B200DPF_OK;
+}
+
+int b200dpf_destroy(b200dpf_ctx *c)
+{
+    if (!c) return B200DPF_OK;
+    DeviceGuard guard(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->d_table) cudaFree(c->d_table);
+    if (c->d_keys) cudaFree(c->d_keys);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B200DPF_OK;
+}
+
+int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, int32_t *out)
+{
+    int rc = check_eval_args(c, keys, nkeys, prf, out);
+    if (rc) return rc;
+    for (int64_t b = 0; b < nkeys; b++)
+        if (host::key_n(keys + b * host::KEY_WORDS) != c->n)
+            return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
+                        (long long)host::key_n(keys + b * host::KEY_WORDS), (long long)c->n);
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    if ((size_t)nkeys > c->keys_cap) {
+        if (c->d_keys) cudaFree(c->d_keys);
+        c->d_keys = nullptr;
+        c->keys_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->d_keys, (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t)));
+        c->keys_cap = (size_t)nkeys;
+    }
+    const size_t out_elems = (size_t)nkeys * c->entry_size;
+    if (out_elems > c->out_cap) {
+        if (c->d_out) cudaFree(c->d_out);
+        c->d_out = nullptr;
+        c->out_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->d_out, out_elems * sizeof(int32_t)));
+        c->out_cap = out_elems;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_keys, keys, (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t),
+                             cudaMemcpyHostToDevice, c->stream));
+    rc = run_eval(c, c->d_keys, nkeys, prf, c->d_out, c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return B200DPF_OK;
+}
+
+int b200dpf_eval_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *out_dev, void *cuda_stream)
+{
+    int rc = check_eval_args(c, keys_dev, nkeys, prf, out_dev);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    return run_eval(c, keys_dev, nkeys, prf, out_dev, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int b200dpf_expand_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *shares_dev, void *cuda_stream)
+{
+    int rc = check_eval_args(c, keys_dev, nkeys, prf, shares_dev);
+    if (rc) return rc;
+    if (c->shard_count != 1) return fail(B200DPF_ESTATE, "expand needs an unsharded context");
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    LaunchPlan plan;
+    rc = plan_launch(c, prf, 1, nkeys, &plan);
+    if (rc) return rc;
+    rc = ensure_counters(c, (size_t)plan.p.key_groups);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, (size_t)plan.p.key_groups * sizeof(uint32_t), stream));
+    plan.p.keys = reinterpret_cast<const uint4 *>(keys_dev);
+    plan.p.shares = reinterpret_cast<uint32_t *>(shares_dev);
+    plan.p.counters = c->d_counters;
+    CUDA_TRY(launch_eval(prf, 1, plan.p, plan.grid, plan.smem, stream));
+    c->last_launches = 1;
+    return B200DPF_OK;
+}
+
+int64_t b200dpf_ctx_n(const b200dpf_ctx *c) { return c ? c->n : -1; }
+int b200dpf_ctx_entry_size(const b200dpf_ctx *c) { return c ? c->entry_size : -1; }
+int b200dpf_ctx_device(const b200dpf_ctx *c) { return c ? c->device : -1; }
+int b200dpf_ctx_last_launches(const b200dpf_ctx *c) { return c ? c->last_launches : -1; }
+
+int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *c, int s)
+{
+    if (!c || s < 0 || s > 16) return fail(B200DPF_EINVAL, "subtree log2 out of range");
+    c->s_override = s;
+    return B200DPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,207 @@
+/*
+ * dpf_cpp_ext.cpp -- the `dpf_cpp` PyTorch extension module.
+ *
+ * Same pybind surface as the reference's dpf_wrapper.cu:188-204 (five
+ * functions, six integer attributes, same argument order and types, results as
+ * CPU int32 tensors), so the reference's dpf.py / sample.py / benchmark.py run
+ * against it unchanged.  All work is delegated to the C ABI in
+ * include/b200dpf.h; this file only converts tensors to pointers.
+ *
+ * Differences from the reference module, all additive:
+ *   - eval_init accepts any entry size and any dtype; eval_gpu accepts any
+ *     number of keys (the reference asserts 16 columns and exactly 512 keys);
+ *   - errors surface as Python exceptions (RuntimeError) instead of assert /
+ *     exit (dpf_wrapper.cu:7-15);
+ *   - extra entry points: gen_batch, eval_gpu_packed, eval_init_sharded,
+ *     expand_gpu, version; attribute NATIVE_SHAPES = 1 advertises them.
+ */
+#include <torch/extension.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200dpf.h"
+
+namespace {
+
+constexpr int kKeyWords = B200DPF_KEY_WORDS;
+
+void check(int rc, const char *what)
+{
+    if (rc != B200DPF_OK) throw std::runtime_error(std::string(what) + ": " + b200dpf_last_error());
+}
+
+b200dpf_ctx *ctx_of(const std::vector<void *> &buffers)
+{
+    if (buffers.empty() || buffers[0] == nullptr) throw std::runtime_error("dpf_cpp: empty buffer list (call eval_init first)");
+    return static_cast<b200dpf_ctx *>(buffers[0]);
+}
+
+const int32_t *key_ptr(const at::Tensor &key)
+{
+    TORCH_CHECK(key.device().is_cpu(), "dpf_cpp: keys must be CPU tensors");
+    TORCH_CHECK(key.scalar_type() == at::kInt && key.numel() == kKeyWords && key.is_contiguous(),
+                "dpf_cpp: a key is a contiguous int32 tensor of 524 elements");
+    return key.data_ptr<int32_t>();
+}
+
+/* dpf_wrapper.cu:49-68 */
+std::vector<at::Tensor> gen(int64_t k, int64_t n, const std::string &seed, int prf)
+{
+    at::Tensor a = torch::zeros({kKeyWords}, at::kInt);
+    at::Tensor b = torch::zeros({kKeyWords}, at::kInt);
+    check(b200dpf_gen(k, n, reinterpret_cast<const uint8_t *>(seed.data()), seed.size(), prf,
+                      a.data_ptr<int32_t>(), b.data_ptr<int32_t>()),
+          "gen");
+    return {a, b};
+}
+
+/* batched keygen: alphas int64[B], seeds int64[B] (low 32 bits used) -> two int32[B,524] tensors */
+std::vector<at::Tensor> gen_batch(const at::Tensor &alphas, int64_t n, const at::Tensor &seeds, int prf, int nthreads)
+{
+    at::Tensor al = alphas.to(at::kLong).contiguous().cpu();
+    at::Tensor sd = seeds.to(at::kLong).contiguous().cpu();
+    TORCH_CHECK(al.dim() == 1 && sd.sizes() == al.sizes(), "gen_batch: alphas and seeds are 1-D of equal length");
+    const int64_t count = al.numel();
+    std::vector<uint32_t> s32((size_t)count);
+    for (int64_t i = 0; i < count; i++) s32[(size_t)i] = (uint32_t)sd.data_ptr<int64_t>()[i];
+    at::Tensor a = torch::zeros({count, kKeyWords}, at::kInt);
+    at::Tensor b = torch::zeros({count, kKeyWords}, at::kInt);
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_gen_batch(al.data_ptr<int64_t>(), s32.data(), count, n, prf, nthreads, a.data_ptr<int32_t>(),
+                                b.data_ptr<int32_t>()),
+              "gen_batch");
+    }
+    return {a, b};
+}
+
+/* dpf_wrapper.cu:70-84 */
+at::Tensor eval_cpu(const at::Tensor &key, int prf)
+{
+    const int32_t *k = key_ptr(key);
+    const int64_t n = b200dpf_key_n(k);
+    TORCH_CHECK(n > 0, "eval_cpu: malformed key");
+    at::Tensor result = torch::empty({n}, at::kInt);
+    check(b200dpf_eval_cpu(k, prf, result.data_ptr<int32_t>()), "eval_cpu");
+    return result;
+}
+
+std::vector<void *> eval_init_sharded(const at::Tensor &table, int device, int shard_rank, int shard_count)
+{
+    TORCH_CHECK(table.dim() == 2, "eval_init: table must be [num_entries, entry_size]");
+    /* dpf_wrapper.cu:107 converts each element with item<int>(); one vectorised cast here */
+    at::Tensor t = table.to(at::kInt).contiguous();
+    b200dpf_ctx *ctx = nullptr;
+    check(b200dpf_create(&ctx, t.data_ptr<int32_t>(), t.size(0), (int)t.size(1), device, shard_rank, shard_count),
+          "eval_init");
+    return {static_cast<void *>(ctx)};
+}
+
+/* dpf_wrapper.cu:93-132 */
+std::vector<void *> eval_init(const at::Tensor &table) { return eval_init_sharded(table, 0, 0, 1); }
+
+/* dpf_wrapper.cu:86-91 */
+void eval_free(const std::vector<void *> &buffers)
+{
+    if (!buffers.empty() && buffers[0]) b200dpf_destroy(static_cast<b200dpf_ctx *>(buffers[0]));
+}
+
+/* keys as one int32[B,524] CPU tensor -> int32[B,E] CPU tensor */
+at::Tensor eval_gpu_packed(const at::Tensor &keys, const std::vector<void *> &buffers, int prf)
+{
+    b200dpf_ctx *ctx = ctx_of(buffers);
+    TORCH_CHECK(keys.device().is_cpu() && keys.scalar_type() == at::kInt && keys.dim() == 2 &&
+                    keys.size(1) == kKeyWords && keys.is_contiguous(),
+                "eval_gpu_packed: keys must be a contiguous CPU int32 tensor [B, 524]");
+    const int64_t nkeys = keys.size(0);
+    at::Tensor result = torch::empty({nkeys, (int64_t)b200dpf_ctx_entry_size(ctx)}, at::kInt);
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_eval(ctx, keys.data_ptr<int32_t>(), nkeys, prf, result.data_ptr<int32_t>()), "eval_gpu");
+    }
+    return result;
+}
+
+/* dpf_wrapper.cu:134-186.  The reference's dpf.py pads short batches by
+ * repeating the LAST key object (dpf.py:126); trailing repeats of one tensor
+ * are evaluated once and their rows replicated. */
+at::Tensor eval_gpu(const std::vector<at::Tensor> &keys, const std::vector<void *> &buffers, int64_t n, int prf)
+{
+    b200dpf_ctx *ctx = ctx_of(buffers);
+    TORCH_CHECK(!keys.empty(), "eval_gpu: no keys");
+    TORCH_CHECK(n == b200dpf_ctx_n(ctx), "eval_gpu: n does not match the initialised table");
+    const int64_t total = (int64_t)keys.size();
+    int64_t unique = total;
+    while (unique > 1 && keys[(size_t)unique - 1].unsafeGetTensorImpl() == keys[(size_t)unique - 2].unsafeGetTensorImpl()) unique--;
+    const int64_t esz = b200dpf_ctx_entry_size(ctx);
+    std::vector<int32_t> packed((size_t)unique * kKeyWords);
+    for (int64_t i = 0; i < unique; i++)
+        std::memcpy(packed.data() + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
+    at::Tensor result = torch::empty({total, esz}, at::kInt);
+    int32_t *r = result.data_ptr<int32_t>();
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_eval(ctx, packed.data(), unique, prf, r), "eval_gpu");
+    }
+    for (int64_t i = unique; i < total; i++) std::memcpy(r + i * esz, r + (unique - 1) * esz, sizeof(int32_t) * (size_t)esz);
+    return result;
+}
+
+/* device-resident evaluation on the current torch stream handle passed as an integer */
+void eval_gpu_device(int64_t keys_ptr, int64_t nkeys, const std::vector<void *> &buffers, int prf, int64_t out_ptr,
+                     int64_t stream)
+{
+    check(b200dpf_eval_device(ctx_of(buffers), reinterpret_cast<const void *>(keys_ptr), nkeys, prf,
+                              reinterpret_cast<void *>(out_ptr), reinterpret_cast<void *>(stream)),
+          "eval_gpu_device");
+}
+
+void expand_gpu_device(int64_t keys_ptr, int64_t nkeys, const std::vector<void *> &buffers, int prf, int64_t out_ptr,
+                       int64_t stream)
+{
+    check(b200dpf_expand_device(ctx_of(buffers), reinterpret_cast<const void *>(keys_ptr), nkeys, prf,
+                                reinterpret_cast<void *>(out_ptr), reinterpret_cast<void *>(stream)),
+          "expand_gpu_device");
+}
+
+int last_launches(const std::vector<void *> &buffers) { return b200dpf_ctx_last_launches(ctx_of(buffers)); }
+
+void set_subtree_log2(const std::vector<void *> &buffers, int s)
+{
+    check(b200dpf_ctx_set_subtree_log2(ctx_of(buffers), s), "set_subtree_log2");
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+    /* the reference surface, dpf_wrapper.cu:190-203 */
+    m.def("gen", &gen, "dpf gen");
+    m.def("eval_cpu", &eval_cpu, "dpf eval cpu");
+    m.def("eval_gpu", &eval_gpu, "dpf eval gpu");
+    m.def("eval_init", &eval_init, "dpf eval init");
+    m.def("eval_free", &eval_free, "dpf eval free");
+
+    m.attr("ENTRY_SIZE") = py::int_(B200DPF_DEFAULT_ENTRY_SIZE);
+    m.attr("BATCH_SIZE") = py::int_(B200DPF_DEFAULT_BATCH_SIZE);
+    m.attr("PRF_DUMMY") = py::int_((int)B200DPF_PRF_DUMMY);
+    m.attr("PRF_SALSA20") = py::int_((int)B200DPF_PRF_SALSA20);
+    m.attr("PRF_CHACHA20") = py::int_((int)B200DPF_PRF_CHACHA20);
+    m.attr("PRF_AES128") = py::int_((int)B200DPF_PRF_AES128);
+
+    /* additions */
+    m.attr("NATIVE_SHAPES") = py::int_(1);
+    m.def("version", []() { return std::string(b200dpf_version()); });
+    m.def("gen_batch", &gen_batch, "batched multi-threaded keygen", py::arg("alphas"), py::arg("n"), py::arg("seeds"),
+          py::arg("prf"), py::arg("nthreads") = 0);
+    m.def("eval_init_sharded", &eval_init_sharded, "eval_init for one entry-range shard", py::arg("table"),
+          py::arg("device"), py::arg("shard_rank"), py::arg("shard_count"));
+    m.def("eval_gpu_packed", &eval_gpu_packed, "eval_gpu with keys as one [B,524] tensor");
+    m.def("eval_gpu_device", &eval_gpu_device, "device-resident asynchronous evaluation");
+    m.def("expand_gpu_device", &expand_gpu_device, "device-resident share-vector expansion");
+    m.def("last_launches", &last_launches);
+    m.def("set_subtree_log2", &set_subtree_log2);
+}

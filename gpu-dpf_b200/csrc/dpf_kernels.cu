@@ -1,0 +1,356 @@
+/*
+ * dpf_kernels.cu -- sm_100a kernels of the DPF evaluation engine.
+ *
+ * One kernel does the whole hot path of the reference's dpf_hybrid_kernel
+ * (dpf_gpu/dpf/dpf_hybrid.cu:38-256): GGM-tree expansion of every key over the
+ * full domain, fused with the inner product against the table, plus the
+ * reduction -- but organised for Blackwell rather than translated:
+ *
+ *   work item   = (group of 32 keys) x (one 2^s-leaf subtree).  A warp owns a
+ *                 work item; LANE = KEY.  All 32 lanes walk the same tree shape,
+ *                 so control flow is warp-uniform and every table row a warp
+ *                 needs is ONE broadcast 128-bit load shared by 32 keys (the
+ *                 reference re-reads the table once per key).
+ *   expansion   = per-thread depth-first search: a node's two children are
+ *                 produced together in registers (shared AES key schedule /
+ *                 shared first-round quarter rounds), the right child parks in a
+ *                 per-thread shared-memory slot (one slot per tree height), the
+ *                 left child is descended into.  No global scratch, no
+ *                 __syncthreads in the main loop (the reference ping-pongs two
+ *                 global stacks with two barriers per step).
+ *   MAC         = only the low 32 bits of a leaf survive (dpf_wrapper.cu:182),
+ *                 so the product is 32-bit IMADs against an int32 table stored
+ *                 in breadth-first leaf order (4x less table traffic than the
+ *                 reference's 128-bit table, ~20x fewer MAC instructions).
+ *   corrections = the 32 keys' correction words live in shared memory, laid out
+ *                 [level][bank][bit][key] so a warp's 16-byte reads are
+ *                 conflict free.
+ *   AES         = T-table AES with the four tables replicated per bank in
+ *                 shared memory (4 x 32 KiB): lane L only ever touches bank L,
+ *                 so lookups are conflict-free, and the shared address of a
+ *                 lookup is formed by ONE PRMT (byte insert into a 64 KiB-aligned
+ *                 base) + the LDS immediate offset.
+ *   scheduling  = persistent blocks; warps draw subtrees from a per-key-group
+ *                 ticket counter (atomicAdd), blocks migrate to the next key
+ *                 group when theirs runs dry, partial sums leave through
+ *                 red.global.add.u32.
+ */
+#include "dpf_kernels.cuh"
+
+#include "dpf_core.cuh"
+
+namespace b200dpf {
+
+namespace {
+
+__constant__ uint32_t c_te0[256];
+
+/* ---- AES table policy on the device -------------------------------------- */
+struct AesSmemTables {
+    /* shared-window address of (table region + lane*4); the region base is a
+     * multiple of 64 KiB, so byte 1 of this value is zero. */
+    uint32_t lanebase;
+
+    template <int K, int BYTE>
+    __device__ __forceinline__ uint32_t te(uint32_t word) const
+    {
+        /* address = lanebase with byte 1 replaced by the index byte:
+         * entry v of table K for lane L sits at v*256 + (K&1)*128 + (K>>1)*65536 + L*4 */
+        const uint32_t addr = __byte_perm(word, lanebase, 0x7604u | (BYTE << 4));
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"((K & 1) * 128 + (K >> 1) * 65536));
+        return v;
+    }
+};
+
+struct NoTables {
+    template <int K, int BYTE>
+    __device__ __forceinline__ uint32_t te(uint32_t) const { return 0; }
+};
+
+template <int PRF> struct TablePolicy { typedef NoTables type; };
+template <> struct TablePolicy<PRF_AES128> { typedef AesSmemTables type; };
+
+/* ---- per-thread environment for the shared traversal code ---------------- */
+template <int PRF, int NV, int THREADS, int MODE>
+struct DevEnv {
+    typename TablePolicy<PRF>::type ta;
+    const uint4 *cw_lane;       /* &cw_s[lane]; entry (level,bank,bit) at +((level*2+bank)*2+bit)*32 */
+    const uint32_t *cwlo_lane;  /* &cwlo_s[lane]; entry (bank,bit) at +(bank*2+bit)*32 */
+    uint4 *stack_lo, *stack_hi; /* pre-offset by tid; level l at +l*THREADS */
+    int stack_split;
+    const uint4 *rows;          /* first row of the current subtree, at this pass's column */
+    uint32_t row_stride_v;
+    uint32_t acc[4 * NV];
+    uint4 ra[NV], rb[NV];
+    /* expand mode */
+    uint32_t *share_row;        /* shares + key*n */
+    uint32_t pos_base;          /* global leaf position of the subtree's first leaf */
+    int depth;
+    bool key_valid;
+
+    __device__ __forceinline__ Seed cw(int level, uint32_t bank, uint32_t bit) const
+    {
+        const uint4 v = cw_lane[((level * 2 + (int)bank) * 2 + (int)bit) * 32];
+        return make_seed(v.x, v.y, v.z, v.w);
+    }
+    __device__ __forceinline__ uint32_t cw_lo(uint32_t bank, uint32_t bit) const
+    {
+        return cwlo_lane[(bank * 2 + bit) * 32];
+    }
+    __device__ __forceinline__ uint4 *slot(int h) const
+    {
+        const int l = h - 1;
+        return (l < stack_split ? stack_lo : stack_hi) + l * THREADS;
+    }
+    __device__ __forceinline__ void push(int h, const Seed &s) const
+    {
+        *slot(h) = make_uint4(s.x, s.y, s.z, s.w);
+    }
+    __device__ __forceinline__ Seed pop(int h) const
+    {
+        const uint4 v = *slot(h);
+        return make_seed(v.x, v.y, v.z, v.w);
+    }
+    __device__ __forceinline__ void leaf_prefetch(uint32_t local_pos)
+    {
+        if (MODE == 0) {
+            const uint4 *r = rows + (size_t)local_pos * row_stride_v;
+#pragma unroll
+            for (int j = 0; j < NV; j++) ra[j] = __ldg(r + j);
+#pragma unroll
+            for (int j = 0; j < NV; j++) rb[j] = __ldg(r + row_stride_v + j);
+        }
+    }
+    __device__ __forceinline__ void leaf_pair(uint32_t local_pos, uint32_t v0, uint32_t v1)
+    {
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                acc[4 * j + 0] += v0 * ra[j].x + v1 * rb[j].x;
+                acc[4 * j + 1] += v0 * ra[j].y + v1 * rb[j].y;
+                acc[4 * j + 2] += v0 * ra[j].z + v1 * rb[j].z;
+                acc[4 * j + 3] += v0 * ra[j].w + v1 * rb[j].w;
+            }
+        } else if (key_valid) {
+            /* leaf position p holds index bitrev_depth(p) */
+            const uint32_t p = pos_base + local_pos;
+            share_row[__brev(p) >> (32 - depth)] = v0;
+            share_row[__brev(p + 1) >> (32 - depth)] = v1;
+        }
+    }
+};
+
+template <int PRF> struct KernelShape { enum { THREADS = 256, MIN_BLOCKS = 2 }; };
+template <> struct KernelShape<PRF_AES128> { enum { THREADS = 384, MIN_BLOCKS = 1 }; };
+
+extern __shared__ __align__(16) unsigned char g_dyn_smem[];
+
+template <int PRF, int NV, int MODE>
+__global__ void __launch_bounds__(KernelShape<PRF>::THREADS, KernelShape<PRF>::MIN_BLOCKS)
+dpf_eval_kernel(const __grid_constant__ EvalParams p)
+{
+    constexpr int THREADS = KernelShape<PRF>::THREADS;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    uint4 *cw_s = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_cw);
+    uint32_t *cwlo_s = reinterpret_cast<uint32_t *>(g_dyn_smem + p.off_cwlo);
+    uint4 *root_s = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_root);
+    volatile int *flag_s = reinterpret_cast<volatile int *>(g_dyn_smem + p.off_flag);
+
+    DevEnv<PRF, NV, THREADS, MODE> env;
+    env.cw_lane = cw_s + lane;
+    env.cwlo_lane = cwlo_s + lane;
+    env.stack_lo = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_stack_lo) + tid;
+    env.stack_hi = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_stack_hi) + tid - p.stack_split * THREADS;
+    env.stack_split = p.stack_split;
+    env.row_stride_v = p.row_stride_v;
+    env.depth = p.depth;
+
+    if constexpr (PRF == PRF_AES128) {
+        /* replicate Te0..Te3 across the 32 banks: entry v, lane L */
+        const uint32_t tab = (uint32_t)__cvta_generic_to_shared(g_dyn_smem + p.off_tab);
+        if ((tab & 0xffffu) != 0) __trap();   /* layout contract with the host planner */
+        for (int i = tid; i < 256 * 32; i += THREADS) {
+            const uint32_t v = c_te0[i >> 5];
+            unsigned char *e = g_dyn_smem + p.off_tab + (i >> 5) * 256 + (i & 31) * 4;
+            *reinterpret_cast<uint32_t *>(e) = v;
+            *reinterpret_cast<uint32_t *>(e + 128) = __funnelshift_l(v, v, 8);
+            *reinterpret_cast<uint32_t *>(e + 65536) = __funnelshift_l(v, v, 16);
+            *reinterpret_cast<uint32_t *>(e + 65536 + 128) = __funnelshift_l(v, v, 24);
+        }
+        env.ta.lanebase = tab + lane * 4;
+    }
+
+    for (int j = 0; j < p.key_groups; j++) {
+        const int kg = (int)((blockIdx.x + (unsigned)j) % (unsigned)p.key_groups);
+
+        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(p.counters + kg) < p.nsub) ? 1 : 0;
+        __syncthreads();
+        const bool has_work = (*flag_s != 0);
+        if (has_work) {
+            /* correction words of this key group -> shared, [level][bank][bit][key] */
+            const int per_key = p.depth * 4;
+            for (int i = tid; i < per_key * 32; i += THREADS) {
+                const int k = i / per_key;            /* key within the group   */
+                const int e = i - k * per_key;        /* (bank, level, bit)     */
+                const int bank = e / (p.depth * 2);
+                const int lb = e - bank * (p.depth * 2);   /* 2*level + bit       */
+                int key = kg * 32 + k;
+                if (key >= p.nkeys) key = p.nkeys - 1;
+                const uint4 v = __ldg(p.keys + (size_t)key * 131 + (bank ? 65 : 1) + lb);
+                const int level = lb >> 1, bit = lb & 1;
+                cw_s[((level * 2 + bank) * 2 + bit) * 32 + k] = v;
+                if (level == 0) cwlo_s[(bank * 2 + bit) * 32 + k] = v.x;
+            }
+            if (tid < 32) {
+                int key = kg * 32 + tid;
+                if (key >= p.nkeys) key = p.nkeys - 1;
+                root_s[tid] = __ldg(p.keys + (size_t)key * 131 + 129);
+            }
+        }
+        __syncthreads();
+        if (!has_work) continue;
+
+        const int key = kg * 32 + lane;
+        env.key_valid = key < p.nkeys;
+        if (MODE == 0) {
+#pragma unroll
+            for (int e = 0; e < 4 * NV; e++) env.acc[e] = 0;
+        } else {
+            env.share_row = p.shares + (size_t)(env.key_valid ? key : 0) * p.n;
+        }
+        const uint4 rv = root_s[lane];
+        const Seed root = make_seed(rv.x, rv.y, rv.z, rv.w);
+
+        for (;;) {
+            uint32_t q = 0;
+            if (lane == 0) q = atomicAdd(p.counters + kg, 1u);
+            q = __shfl_sync(0xffffffffu, q, 0);
+            if (q >= p.nsub) break;
+            env.rows = p.table + ((size_t)q << p.s) * p.row_stride_v + p.col_off_v;
+            env.pos_base = (p.sub_first + q) << p.s;
+            const Seed r = walk_to_subtree<PRF>(env, root, p.depth, p.s, p.sub_first + q);
+            eval_subtree<PRF>(env, r, p.s);
+        }
+
+        if (MODE == 0 && env.key_valid) {
+            uint32_t *o = p.out + (size_t)key * p.out_stride + p.col_off;
+#pragma unroll
+            for (int e = 0; e < 4 * NV; e++)
+                if ((uint32_t)e < p.ncols) atomicAdd(o + e, env.acc[e]);
+        }
+        __syncthreads();   /* everyone done with this group's correction words */
+    }
+}
+
+__global__ void probe_smem_kernel(uint32_t *out)
+{
+    if (threadIdx.x == 0) *out = (uint32_t)__cvta_generic_to_shared(g_dyn_smem);
+}
+
+__global__ void permute_table_kernel(const int32_t *__restrict__ stage, int32_t *__restrict__ table,
+                                     uint64_t rows, int bits, int cols, int stride)
+{
+    const uint64_t total = rows * (uint64_t)cols;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t q = i / (uint64_t)cols;
+        const int c = (int)(i - q * (uint64_t)cols);
+        const uint64_t src = bits ? (uint64_t)(__brev((uint32_t)q) >> (32 - bits)) : 0;
+        table[q * (uint64_t)stride + c] = stage[src * (uint64_t)cols + c];
+    }
+}
+
+template <int PRF, int MODE>
+cudaError_t launch_one(const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
+{
+    auto kern = dpf_eval_kernel<PRF, 4, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    /* the kernels live in shared memory; L1 only sees broadcast table rows */
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, KernelShape<PRF>::THREADS, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int PRF, int MODE>
+cudaError_t max_smem_one(int *bytes)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, dpf_eval_kernel<PRF, 4, MODE>);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    *bytes = optin - (int)a.sharedSizeBytes;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+int eval_threads(int prf) { return prf == PRF_AES128 ? (int)KernelShape<PRF_AES128>::THREADS : (int)KernelShape<PRF_DUMMY>::THREADS; }
+int eval_min_blocks(int prf) { return prf == PRF_AES128 ? (int)KernelShape<PRF_AES128>::MIN_BLOCKS : (int)KernelShape<PRF_DUMMY>::MIN_BLOCKS; }
+
+cudaError_t probe_dynamic_smem_base(uint32_t *base, cudaStream_t stream)
+{
+    uint32_t *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    probe_smem_kernel<<<1, 32, 16, stream>>>(d);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(base, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    return e;
+}
+
+cudaError_t upload_aes_table(const uint32_t *te0_256)
+{
+    return cudaMemcpyToSymbol(c_te0, te0_256, 256 * sizeof(uint32_t));
+}
+
+cudaError_t launch_eval(int prf, int mode, const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
+{
+#define DPF_DISPATCH(P)                                                     \
+    case P:                                                                 \
+        return mode == 0 ? launch_one<P, 0>(p, grid, smem, stream) : launch_one<P, 1>(p, grid, smem, stream);
+    switch (prf) {
+        DPF_DISPATCH(PRF_DUMMY)
+        DPF_DISPATCH(PRF_SALSA20)
+        DPF_DISPATCH(PRF_CHACHA20)
+        DPF_DISPATCH(PRF_AES128)
+    default: return cudaErrorInvalidValue;
+    }
+#undef DPF_DISPATCH
+}
+
+cudaError_t eval_max_smem(int prf, int mode, int *bytes)
+{
+#define DPF_DISPATCH(P)                                                     \
+    case P:                                                                 \
+        return mode == 0 ? max_smem_one<P, 0>(bytes) : max_smem_one<P, 1>(bytes);
+    switch (prf) {
+        DPF_DISPATCH(PRF_DUMMY)
+        DPF_DISPATCH(PRF_SALSA20)
+        DPF_DISPATCH(PRF_CHACHA20)
+        DPF_DISPATCH(PRF_AES128)
+    default: return cudaErrorInvalidValue;
+    }
+#undef DPF_DISPATCH
+}
+
+cudaError_t launch_permute_table(const int32_t *stage, int32_t *table, uint64_t rows, int bits,
+                                 int cols, int stride, cudaStream_t stream)
+{
+    const uint64_t total = rows * (uint64_t)cols;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid < 1) grid = 1;
+    permute_table_kernel<<<grid, 256, 0, stream>>>(stage, table, rows, bits, cols, stride);
+    return cudaGetLastError();
+}
+
+}  // namespace b200dpf

@@ -1,0 +1,67 @@
+/*
+ * dpf_kernels.cuh -- launch interface between the C-ABI layer (dpf_capi.cu)
+ * and the sm_100a kernels (dpf_kernels.cu).  Plain structs, no torch.
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200dpf {
+
+/* Parameters of one evaluation launch (one pass over <= 16*NVMAX columns). */
+struct EvalParams {
+    const uint4 *keys;        /* [nkeys][131] 128-bit slots, reference wire format      */
+    int nkeys;
+    int key_groups;           /* ceil(nkeys / 32): one lane per key, 32 keys per warp   */
+    const uint4 *table;       /* this shard's rows in breadth-first leaf order          */
+    uint32_t row_stride_v;    /* uint4 per table row (padded entry size / 4)            */
+    uint32_t col_off_v;       /* first uint4 column of this pass                        */
+    uint32_t *out;            /* [nkeys][out_stride] uint32, pre-zeroed                 */
+    uint32_t out_stride;
+    uint32_t col_off;         /* first int32 column of this pass                        */
+    uint32_t ncols;           /* valid int32 columns in this pass (<= 4*NV)             */
+    int depth;                /* log2 n                                                 */
+    int s;                    /* log2 leaves per work item (one warp = 32 keys x 2^s)   */
+    uint32_t sub_first;       /* breadth-first index of the shard's first 2^s-subtree   */
+    uint32_t nsub;            /* number of 2^s-subtrees in this shard                   */
+    uint32_t *counters;       /* [key_groups] work-item tickets, pre-zeroed             */
+    /* expand mode (non-fused): shares[key][index], natural order                      */
+    uint32_t *shares;
+    uint64_t n;
+    /* dynamic shared memory plan (byte offsets from the dynamic smem base)            */
+    uint32_t off_cw;          /* uint4 [depth][2 banks][2 bits][32 keys]                */
+    uint32_t off_cwlo;        /* uint32 [2][2][32]: low words of the level-0 words      */
+    uint32_t off_root;        /* uint4 [32] root seeds                                  */
+    uint32_t off_flag;        /* int                                                    */
+    uint32_t off_stack_lo;    /* pending-sibling stack, levels [0, stack_split)         */
+    uint32_t off_stack_hi;    /* levels [stack_split, s-1)                              */
+    int stack_split;
+    uint32_t off_tab;         /* AES tables: 128 KiB whose shared-window address is a
+                                 multiple of 64 KiB                                     */
+};
+
+/* Threads per block / minimum blocks per SM chosen for each PRF kernel. */
+int eval_threads(int prf);
+int eval_min_blocks(int prf);
+
+/* Shared-window address of the first dynamic shared memory byte (probed). */
+cudaError_t probe_dynamic_smem_base(uint32_t *base, cudaStream_t stream);
+
+/* Upload the AES T-table to this device's constant memory. */
+cudaError_t upload_aes_table(const uint32_t *te0_256);
+
+/* One pass of the fused evaluation (mode 0) or the share expansion (mode 1).
+ * grid = number of persistent blocks; smem_bytes = dynamic shared memory. */
+cudaError_t launch_eval(int prf, int mode, const EvalParams &p, int grid, size_t smem_bytes,
+                        cudaStream_t stream);
+
+/* Maximum dynamic shared memory the evaluation kernel may be given. */
+cudaError_t eval_max_smem(int prf, int mode, int *bytes);
+
+/* table[q][c] = stage[bitrev_bits(q)][c] for q < rows, c < cols; padded columns
+ * [cols, stride) are left untouched (pre-zeroed). */
+cudaError_t launch_permute_table(const int32_t *stage, int32_t *table, uint64_t rows, int bits,
+                                 int cols, int stride, cudaStream_t stream);
+
+}  // namespace b200dpf

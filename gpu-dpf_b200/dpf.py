@@ -1,0 +1,278 @@
+"""dpf.DPF -- the reference's Python API (dpf.py:35-137) on the B200-native engine.
+
+Same class, method names, argument meaning and exceptions as the reference, so
+`sample.py` and `benchmark.py` written against it keep working:
+
+    d = DPF(prf=DPF.PRF_AES128)
+    k1, k2 = d.gen(index, n)        # client: two int32[524] CPU key tensors
+    d.eval_init(table)              # server: upload [n, entry_size] table
+    shares = d.eval_gpu([k1, ...])  # server: int32 [len(keys), entry_size] on the CPU
+
+What differs is behind the boundary: `dpf_cpp` here is the pybind shim over
+include/b200dpf.h (hand-written sm_100a kernels), tables may have any entry
+size, batches may have any length (no pad-to-512 round trip, no pad-to-16
+columns), and one process can own an entry-range shard of the table
+(`DPF(prf, device=d, shard=(rank, count))`) whose partial results add mod 2^32.
+
+The module-level test_* / *_perf helpers mirror the reference's self-tests
+(dpf.py:139-356): same names and defaults, same pass criteria.
+"""
+import os
+import random
+import sys
+import time
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if _HERE not in sys.path:
+    sys.path.insert(0, _HERE)
+
+try:
+    import dpf_cpp
+except ImportError as exc:  # fail loudly: there is no Python/CPU stand-in for the kernels
+    raise ImportError(
+        "dpf_cpp extension not built (run `python gpu-dpf_b200/build.py`); "
+        "the DPF engine has no fallback implementation: %s" % exc)
+
+
+class DPF(object):
+
+    PRF_CHACHA20 = dpf_cpp.PRF_CHACHA20
+    PRF_DUMMY = dpf_cpp.PRF_DUMMY
+    PRF_SALSA20 = dpf_cpp.PRF_SALSA20
+    PRF_AES128 = dpf_cpp.PRF_AES128
+
+    ENTRY_SIZE = dpf_cpp.ENTRY_SIZE
+    BATCH_SIZE = dpf_cpp.BATCH_SIZE
+
+    DEFAULT_PRF = dpf_cpp.PRF_AES128
+
+    _PRF_NAMES = {
+        dpf_cpp.PRF_CHACHA20: "CHACHA20",
+        dpf_cpp.PRF_DUMMY: "DUMMY",
+        dpf_cpp.PRF_SALSA20: "SALSA20",
+        dpf_cpp.PRF_AES128: "AES128",
+    }
+
+    def __init__(self, prf=None, device=0, shard=(0, 1)):
+        self.buffers = None
+        self.table_num_entries = None
+        self.table_effective_entry_size = None
+        self.table = None
+        self.device = device
+        self.shard = tuple(shard)
+        self.prf_method = prf if prf is not None else self.DEFAULT_PRF
+        self.prf_method_string = self._PRF_NAMES[self.prf_method]
+
+    # ---- client -----------------------------------------------------------
+    def gen(self, k, n, seed=None):
+        """Two keys for the point function at index k over a domain of n (dpf.py:63-74)."""
+        if seed is None:
+            seed = os.urandom(128)
+        if n & (n - 1) != 0:
+            raise Exception("Table num entries (%d) must be a power of two" % (n))
+        if k >= n:
+            raise Exception("k (%d), the selected element, must be less than n (%d), the number of entries in the table"
+                            % (k, n))
+        return dpf_cpp.gen(k, n, seed, self.prf_method)
+
+    def gen_batch(self, indices, n, seeds=None, nthreads=0):
+        """Keys for many indices at once: two int32 [B, 524] tensors (multi-threaded keygen)."""
+        if n & (n - 1) != 0:
+            raise Exception("Table num entries (%d) must be a power of two" % (n))
+        idx = torch.as_tensor(list(indices), dtype=torch.int64)
+        if idx.numel() and int(idx.max()) >= n:
+            raise Exception("k (%d), the selected element, must be less than n (%d), the number of entries in the table"
+                            % (int(idx.max()), n))
+        if seeds is None:
+            seeds = torch.from_numpy(np.frombuffer(os.urandom(8 * idx.numel()), dtype=np.int64).copy())
+        return dpf_cpp.gen_batch(idx, n, torch.as_tensor(seeds, dtype=torch.int64), self.prf_method, nthreads)
+
+    # ---- server -----------------------------------------------------------
+    def eval_cpu(self, keys, one_hot_only=False):
+        """CPU evaluation (dpf.py:76-86): share vectors, or shares @ table."""
+        if one_hot_only:
+            return torch.stack([dpf_cpp.eval_cpu(k, self.prf_method) for k in keys])
+        if self.table is None:
+            raise Exception("Must call `eval_init` before `eval_cpu` with one_hot_only=False")
+        one_hots = torch.stack([dpf_cpp.eval_cpu(k, self.prf_method) for k in keys])
+        return torch.matmul(one_hots, self.table)
+
+    def eval_init(self, table):
+        """Upload the table (dpf.py:88-113).  Any entry size; no column padding."""
+        self.table = table
+        if self.buffers is not None:
+            dpf_cpp.eval_free(self.buffers)
+            self.buffers = None
+        self.table_num_entries = table.shape[0]
+        self.table_effective_entry_size = table.shape[1]
+        if self.table_num_entries < 128:
+            raise Exception("Table (%d) must have at least 128 elements" % self.table_num_entries)
+        if self.table_num_entries & (self.table_num_entries - 1) != 0:
+            raise Exception("Table num entries (%d) must be a power of two" % (self.table_num_entries))
+        self.buffers = dpf_cpp.eval_init_sharded(table, self.device, self.shard[0], self.shard[1])
+
+    def eval_gpu(self, keys):
+        """Evaluate a batch on the GPU (dpf.py:115-131): int32 [len(keys), entry_size] on the CPU.
+
+        `keys` is a list of int32[524] tensors, or one int32 [B, 524] tensor."""
+        if self.buffers is None:
+            raise Exception("Must call `eval_init` before `eval_gpu`")
+        if isinstance(keys, torch.Tensor):
+            packed = keys.contiguous()
+        else:
+            if len(keys) == 0:
+                return torch.zeros((0, self.table_effective_entry_size), dtype=torch.int32)
+            packed = torch.stack(list(keys))
+        return dpf_cpp.eval_gpu_packed(packed, self.buffers, self.prf_method)
+
+    def eval_gpu_device(self, keys_dev, out_dev=None):
+        """Device-resident, asynchronous variant: keys_dev int32 [B,524] CUDA tensor ->
+        int32 [B, entry_size] CUDA tensor, enqueued on the current torch stream."""
+        if self.buffers is None:
+            raise Exception("Must call `eval_init` before `eval_gpu`")
+        assert keys_dev.is_cuda and keys_dev.dtype == torch.int32 and keys_dev.is_contiguous()
+        if out_dev is None:
+            out_dev = torch.empty((keys_dev.shape[0], self.table_effective_entry_size), dtype=torch.int32,
+                                  device=keys_dev.device)
+        stream = torch.cuda.current_stream(keys_dev.device).cuda_stream
+        dpf_cpp.eval_gpu_device(keys_dev.data_ptr(), keys_dev.shape[0], self.buffers, self.prf_method,
+                                out_dev.data_ptr(), stream)
+        return out_dev
+
+    def expand_gpu_device(self, keys_dev, out_dev=None):
+        """Share vectors on the GPU (the eval_cpu(one_hot_only=True) quantity): int32 [B, n] CUDA tensor."""
+        if self.buffers is None:
+            raise Exception("Must call `eval_init` before `expand_gpu_device`")
+        assert keys_dev.is_cuda and keys_dev.dtype == torch.int32 and keys_dev.is_contiguous()
+        if out_dev is None:
+            out_dev = torch.empty((keys_dev.shape[0], self.table_num_entries), dtype=torch.int32,
+                                  device=keys_dev.device)
+        stream = torch.cuda.current_stream(keys_dev.device).cuda_stream
+        dpf_cpp.expand_gpu_device(keys_dev.data_ptr(), keys_dev.shape[0], self.buffers, self.prf_method,
+                                  out_dev.data_ptr(), stream)
+        return out_dev
+
+    def close(self):
+        if self.buffers is not None:
+            dpf_cpp.eval_free(self.buffers)
+            self.buffers = None
+
+    def __repr__(self):
+        if self.buffers is None:
+            return "DPF(_uninitialized_, prf_method=%s)" % self.prf_method_string
+        return "DPF(entries=%d, entry_size=%d, prf_method=%s)" % (
+            self.table_num_entries, self.table_effective_entry_size, self.prf_method_string)
+
+
+# ---------------------------------------------------------------------------
+# self-tests and perf helpers, mirroring dpf.py:139-356 of the reference
+# ---------------------------------------------------------------------------
+
+def _gen_keys(dpf, batch, N):
+    k1s, k2s, indices = [], [], []
+    for _ in range(batch):
+        indx = random.randint(0, N - 1)
+        indices.append(indx)
+        k1, k2 = dpf.gen(indx, N)
+        k1s.append(k1)
+        k2s.append(k2)
+    return k1s, k2s, indices
+
+
+def _index_table(N, cols=16, dtype=torch.int32):
+    return (torch.arange(N).reshape(N, 1) * cols + torch.arange(cols).reshape(1, cols)).to(dtype)
+
+
+def test_cpu_dpf_one_hot(N=1024):
+    dpf = DPF()
+    K = 42
+    k1, k2 = dpf.gen(K, N)
+    v1 = dpf.eval_cpu([k1], one_hot_only=True)
+    v2 = dpf.eval_cpu([k2], one_hot_only=True)
+    rec = (v1 - v2).numpy()
+    gt = np.zeros(rec.shape)
+    gt[:, K] = 1
+    assert np.linalg.norm(rec - gt) <= 1e-8
+    print("Pass CPU (one-hot only) check.")
+
+
+def test_cpu_dpf(N=1024):
+    dpf = DPF()
+    k1s, k2s, gt_indices = _gen_keys(dpf, 64, N)
+    dpf.table = _index_table(N)   # CPU-only: no device upload needed for eval_cpu
+    a = dpf.eval_cpu(k1s)
+    b = dpf.eval_cpu(k2s)
+    rec = (a - b).numpy()
+    gt = dpf.table[gt_indices, :].numpy()
+    assert np.linalg.norm(rec - gt) <= 1e-8
+    print("Pass CPU check.")
+
+
+def test_gpu_dpf(N=8192):
+    dpf = DPF()
+    k1s, k2s, gt_indices = _gen_keys(dpf, 64, N)
+    table = _index_table(N, dtype=torch.float32)   # the reference feeds a float table here
+    dpf.eval_init(table)
+    a = dpf.eval_gpu(k1s)
+    b = dpf.eval_gpu(k2s)
+    rec = (a - b).numpy()
+    gt = table[gt_indices, :].numpy()
+    assert np.linalg.norm(rec - gt) <= 1e-8
+    print("Pass GPU check.")
+
+
+def test_gpu_dpf_nopad(N=8192, batch=42, entrysize=13):
+    dpf = DPF()
+    k1s, k2s, gt_indices = _gen_keys(dpf, batch, N)
+    table = torch.randint(2 ** 31, (N, entrysize)).int()
+    dpf.eval_init(table)
+    a = dpf.eval_gpu(k1s)
+    b = dpf.eval_gpu(k2s)
+    rec = (a - b).numpy()
+    gt = table[gt_indices, :].numpy()
+    assert np.linalg.norm(rec - gt) <= 1e-8
+    print("Pass GPU (nopad) check.")
+
+
+def test_gpu_dpf_sweep():
+    for n in [128, 256, 512, 1024, 8192]:
+        test_gpu_dpf_nopad(n, batch=random.randint(1, dpf_cpp.BATCH_SIZE * 5 - 1), entrysize=random.randint(1, 16 - 1))
+    print("Pass GPU (sweep) check.")
+
+
+def _perf(kind, N, batch, entrysize, prf):
+    dpf = DPF(prf=prf)
+    k1s, _, _ = _gen_keys(dpf, batch, N)
+    table = torch.rand(N, entrysize).int()
+    dpf.eval_init(table)
+    fn = dpf.eval_gpu if kind == "gpu" else dpf.eval_cpu
+    tstart = time.time()
+    reps = 10
+    for _ in range(reps):
+        fn(k1s)
+    elapsed = time.time() - tstart
+    dpfs_per_sec = batch * reps / elapsed
+    keysize = np.prod(k1s[0].shape) * 4
+    print("%s Key Size: %d bytes, Perf: %d dpfs/sec" % (dpf, keysize, dpfs_per_sec))
+    return dpfs_per_sec
+
+
+def test_gpu_dpf_perf(N=2048, batch=dpf_cpp.BATCH_SIZE, entrysize=16, prf=DPF.DEFAULT_PRF):
+    return _perf("gpu", N, batch, entrysize, prf)
+
+
+def test_cpu_dpf_perf(N=2048, batch=dpf_cpp.BATCH_SIZE, entrysize=16, prf=DPF.DEFAULT_PRF):
+    return _perf("cpu", N, batch, entrysize, prf)
+
+
+if __name__ == "__main__":
+    random.seed(time.time())
+    test_cpu_dpf()
+    test_cpu_dpf_one_hot()
+    test_gpu_dpf()
+    test_gpu_dpf_nopad()
+    test_gpu_dpf_sweep()
+    test_gpu_dpf_perf()

@@ -1,0 +1,173 @@
+/*
+ * b200dpf.h -- C ABI of the B200-native DPF evaluation engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of facebookresearch/GPU-DPF:
+ * batched full-domain evaluation of log(n)-key distributed point functions
+ * fused with the int32 inner product against the server's table.  Everything a
+ * binding of that path needs is here as plain pointers and sizes (no torch, no
+ * C++ types).  The reference reaches the same functionality through the five
+ * pybind functions of dpf_wrapper.cu:188-204; each entry point below names the
+ * reference interface it stands in for.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200DPF_E* code on
+ *     failure; b200dpf_last_error() returns a thread-local message.
+ *   - a key is the reference's wire format: int32[524] == 131 little-endian
+ *     128-bit slots, [0]=depth, [1..64]=cw_1, [65..128]=cw_2, [129]=root seed,
+ *     [130]=n                                  (dpf_wrapper.cu:26-46).
+ *   - PRF ids are the reference's: 0 DUMMY, 1 SALSA20, 2 CHACHA20, 3 AES128
+ *                                              (dpf_wrapper.cu:200-203).
+ *   - results: out[b][e] = int32( sum_i low32(EvaluateFlat(key_b, i)) *
+ *     uint32(table[i][e]) mod 2^32 )           (dpf_base/dpf.h:362-377 +
+ *     dpf_wrapper.cu:178-185 + dpf.py:85-86).
+ *
+ * The GPU entry points require a CUDA device and fail with B200DPF_ECUDA when
+ * none is usable: there is no CPU fallback behind them.
+ */
+#ifndef B200DPF_H
+#define B200DPF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DPF_KEY_WORDS 524          /* int32 words per key (2096 bytes)      */
+#define B200DPF_DEFAULT_ENTRY_SIZE 16  /* dpf_wrapper.cu:18  (MM)               */
+#define B200DPF_DEFAULT_BATCH_SIZE 512 /* dpf_wrapper.cu:21  (BATCH_SIZE)       */
+
+enum {
+    B200DPF_PRF_DUMMY = 0,
+    B200DPF_PRF_SALSA20 = 1,
+    B200DPF_PRF_CHACHA20 = 2,
+    B200DPF_PRF_AES128 = 3
+};
+
+enum {
+    B200DPF_OK = 0,
+    B200DPF_EINVAL = -1,   /* bad argument (shape, power of two, prf id, ...)   */
+    B200DPF_ECUDA = -2,    /* CUDA runtime error or no usable device            */
+    B200DPF_ENOMEM = -3,
+    B200DPF_ESTATE = -4    /* call out of order (e.g. eval before table upload) */
+};
+
+typedef struct b200dpf_ctx b200dpf_ctx;
+
+/* Library identification: "b200dpf <semver> sm_100a". */
+const char *b200dpf_version(void);
+
+/* Thread-local description of the last failure on this thread. */
+const char *b200dpf_last_error(void);
+
+/* ------------------------------------------------------------------------- */
+/* Client side (CPU).                                                         */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Two-server key generation for the point function f(alpha) = 1.
+ * Replaces: dpf_cpp.gen -> gen()                          dpf_wrapper.cu:49-68
+ *           (GenerateSeedsAndCodewordsLog dpf_base/dpf.h:403-464, FlattenCodewords :239-270).
+ * `seed`/`seed_len`: the caller's entropy; like the reference, the generator is
+ * std::mt19937 seeded with the first 4 bytes (little endian), so identical
+ * seeds give keys identical to the reference's.
+ * key_a/key_b: caller-allocated int32[524] each.
+ */
+int b200dpf_gen(int64_t alpha, int64_t n, const uint8_t *seed, size_t seed_len,
+                int prf, int32_t *key_a, int32_t *key_b);
+
+/*
+ * Batched key generation: `count` independent
+ * b200dpf_gen calls spread over `nthreads` host threads (0 = all cores).
+ * alphas[count]; seeds32[count] (one 32-bit generator seed per key);
+ * keys_a/keys_b: int32[count][524].
+ */
+int b200dpf_gen_batch(const int64_t *alphas, const uint32_t *seeds32, int64_t count,
+                      int64_t n, int prf, int nthreads,
+                      int32_t *keys_a, int32_t *keys_b);
+
+/*
+ * One server's share vector on the CPU, natural index order: out[i] =
+ * (int32) low32(EvaluateFlat(key, i)), i < n (n read from the key).
+ * Replaces: dpf_cpp.eval_cpu -> eval_dpf_cpu()            dpf_wrapper.cu:70-84.
+ * This is the API's CPU function, not a fallback for the GPU path.
+ */
+int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n);
+
+/* n stored in a key (slot 130) and its depth (slot 0); -1 if malformed. */
+int64_t b200dpf_key_n(const int32_t *key);
+int b200dpf_key_depth(const int32_t *key);
+
+/* ------------------------------------------------------------------------- */
+/* Server side (GPU, sm_100a).                                                */
+/* ------------------------------------------------------------------------- */
+
+/*
+ * Upload a table and build an evaluation context on CUDA device `device`.
+ * Replaces: dpf_cpp.eval_init -> eval_init()              dpf_wrapper.cu:93-132
+ *           (+ dpf_hybrid_initialize dpf_gpu/dpf/dpf_hybrid.cu:30-36).
+ *
+ * table:        int32 [n][entry_size] row-major, natural index order, host or
+ *               device memory (any pointer cudaMemcpy can read).
+ * n:            power of two, 2 <= n <= 2^31.
+ * entry_size:   1 .. 4096 int32 columns (the reference fixes 16).
+ * shard_rank / shard_count: entry-range sharding.
+ *               shard_count must be a power of two <= n/2; this context then owns
+ *               the GGM subtree under the depth-log2(shard_count) node with
+ *               breadth-first index shard_rank, copies only those n/shard_count
+ *               rows, and b200dpf_eval* returns PARTIAL sums that the caller
+ *               adds (mod 2^32) across shards.  Pass (0, 1) for a whole table.
+ */
+int b200dpf_create(b200dpf_ctx **ctx, const int32_t *table, int64_t n, int entry_size,
+                   int device, int shard_rank, int shard_count);
+
+/* Replaces: dpf_cpp.eval_free -> eval_free()               dpf_wrapper.cu:86-91. */
+int b200dpf_destroy(b200dpf_ctx *ctx);
+
+/*
+ * Evaluate `nkeys` keys against the context's table; host buffers in and out.
+ * Replaces: dpf_cpp.eval_gpu -> eval_gpu()                dpf_wrapper.cu:134-186
+ *           (+ dpf_hybrid<prf>() dpf_gpu/dpf/dpf_hybrid.cu:258-272).
+ * keys: int32[nkeys][524] (host).  out: int32[nkeys][entry_size] (host).
+ * Synchronous: the result is complete on return.  Any nkeys >= 1 (the
+ * reference requires exactly 512).
+ */
+int b200dpf_eval(b200dpf_ctx *ctx, const int32_t *keys, int64_t nkeys, int prf, int32_t *out);
+
+/*
+ * Same computation with DEVICE buffers, enqueued on `cuda_stream` (a
+ * cudaStream_t, may be NULL for the default stream) and NOT synchronised:
+ * for callers that keep keys and results resident (benchmarks, NCCL reduce of
+ * sharded partials).  keys_dev: int32[nkeys][524]; out_dev: int32[nkeys][entry_size].
+ */
+int b200dpf_eval_device(b200dpf_ctx *ctx, const void *keys_dev, int64_t nkeys, int prf,
+                        void *out_dev, void *cuda_stream);
+
+/*
+ * Non-fused full-domain expansion on the GPU (SURVEY.md section 8(f) rank 2;
+ * the role of FUSES_MATMUL=0 in dpf_gpu/dpf/dpf_hybrid.cu:162-165, but in
+ * natural index order): shares_dev[b][i] = low32(EvaluateFlat(key_b, i)) for
+ * this context's shard rows... whole domain only (shard_count must be 1).
+ * keys_dev: int32[nkeys][524]; shares_dev: int32[nkeys][n].
+ */
+int b200dpf_expand_device(b200dpf_ctx *ctx, const void *keys_dev, int64_t nkeys, int prf,
+                          void *shares_dev, void *cuda_stream);
+
+/* Introspection. */
+int64_t b200dpf_ctx_n(const b200dpf_ctx *ctx);
+int b200dpf_ctx_entry_size(const b200dpf_ctx *ctx);
+int b200dpf_ctx_device(const b200dpf_ctx *ctx);
+
+/* Kernels launched by the most recent b200dpf_eval / _eval_device / _expand_device
+ * call on this context (for benchmark accounting). */
+int b200dpf_ctx_last_launches(const b200dpf_ctx *ctx);
+
+/* Algorithm tuning knob, mainly for tests: log2 of the leaves one thread
+ * expands depth-first per work item (0 = automatic). */
+int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *ctx, int s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DPF_H */

@@ -1,0 +1,130 @@
+"""CPU-side product code (keygen, eval_cpu, the C-ABI surface, the dpf.DPF API)
+against the oracle and the golden vectors.  No GPU; no compute calls on the GPU
+entry points beyond checking that they refuse to run without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import b200dpf
+from common import formula_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b200dpf.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200dpf_[a-z0-9_]+)\s*\(", header)) - {"b200dpf_ctx"})
+    assert declared == sorted(b200dpf.SYMBOLS)
+    L = C.CDLL(b200dpf.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in b200dpf.lib().b200dpf_version()
+
+
+def test_gen_matches_golden_keys(golden):
+    for ci, (prf, n, alpha, seed32) in enumerate(golden["case_meta"]):
+        ka, kb = b200dpf.gen(int(alpha), int(n), int(seed32), int(prf))
+        assert np.array_equal(ka, golden["keys_a"][ci])
+        assert np.array_equal(kb, golden["keys_b"][ci])
+
+
+def test_gen_batch_matches_gen(oracle):
+    n, prf = 4096, 3
+    alphas = [0, 1, 17, 4095, 2048, 999]
+    seeds = [5, 6, 7, 8, 9, 2**32 - 1]
+    a, b = b200dpf.gen_batch(alphas, n, seeds, prf, nthreads=3)
+    for i in range(len(alphas)):
+        oa, ob = oracle.gen(alphas[i], n, seeds[i], prf)
+        assert np.array_equal(a[i], oa) and np.array_equal(b[i], ob)
+
+
+def test_eval_cpu_matches_golden_and_oracle(oracle, golden):
+    for ci, (prf, n, alpha, seed32) in enumerate(golden["case_meta"]):
+        prf, n = int(prf), int(n)
+        got = b200dpf.eval_cpu(golden["keys_a"][ci], prf)
+        if n <= 1024:
+            assert np.array_equal(got, golden["share_a_%d" % ci])
+        assert np.array_equal(got, oracle.eval_full(golden["keys_a"][ci], prf))
+
+
+def test_eval_cpu_large_domain(oracle):
+    """n = 2^18: walks across several 2^16-leaf subtrees of the shared traversal code."""
+    n = 1 << 18
+    for prf in (0, 2):
+        ka, kb = b200dpf.gen(123457, n, 77, prf)
+        sa, sb = b200dpf.eval_cpu(ka, prf), b200dpf.eval_cpu(kb, prf)
+        d = (sa.astype(np.int64) - sb.astype(np.int64)) % (1 << 32)
+        assert d[123457] == 1 and np.count_nonzero(d) == 1
+        assert np.array_equal(sa, oracle.eval_full(ka, prf))
+
+
+def test_error_codes():
+    L = b200dpf.lib()
+    a = np.zeros(524, np.int32)
+    b = np.zeros(524, np.int32)
+    assert L.b200dpf_gen(5, 100, b"abcd", 4, 3, a, b) == -1          # n not a power of two
+    assert L.b200dpf_gen(128, 128, b"abcd", 4, 3, a, b) == -1        # alpha >= n
+    assert L.b200dpf_gen(1, 128, b"abcd", 4, 9, a, b) == -1          # bad prf
+    assert b"power-of-two" in L.b200dpf_last_error()
+    assert L.b200dpf_eval_cpu(a, 3, np.zeros(4, np.int32)) == -1     # all-zero key is malformed
+    assert L.b200dpf_key_n(a) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_gpu_entry_points_fail_loudly_without_device():
+    with pytest.raises(b200dpf.B200DPFError, match="no CUDA device"):
+        b200dpf.Context(formula_table(128, 16))
+
+
+def test_python_api_cpu_side():
+    import dpf
+    import dpf_cpp
+    assert (dpf_cpp.ENTRY_SIZE, dpf_cpp.BATCH_SIZE) == (16, 512)
+    assert (dpf_cpp.PRF_DUMMY, dpf_cpp.PRF_SALSA20, dpf_cpp.PRF_CHACHA20, dpf_cpp.PRF_AES128) == (0, 1, 2, 3)
+    for name in ("gen", "eval_cpu", "eval_gpu", "eval_init", "eval_free"):
+        assert callable(getattr(dpf_cpp, name))
+    d = dpf.DPF()
+    assert repr(d) == "DPF(_uninitialized_, prf_method=AES128)"
+    with pytest.raises(Exception, match="power of two"):
+        d.gen(3, 100)
+    with pytest.raises(Exception, match="must be less than n"):
+        d.gen(128, 128)
+    with pytest.raises(Exception, match="Must call `eval_init`"):
+        d.eval_gpu([])
+    with pytest.raises(Exception, match="at least 128"):
+        d.eval_init(torch.zeros(64, 16).int())
+    with pytest.raises(Exception, match="power of two"):
+        d.eval_init(torch.zeros(192, 16).int())
+    k1, k2 = d.gen(42, 1024)
+    assert k1.dtype == torch.int32 and tuple(k1.shape) == (524,)
+    v = d.eval_cpu([k1], one_hot_only=True) - d.eval_cpu([k2], one_hot_only=True)
+    assert v[0, 42] == 1 and v.count_nonzero() == 1
+    dpf.test_cpu_dpf_one_hot()
+    dpf.test_cpu_dpf()
+
+
+def test_python_gen_is_reference_compatible(golden):
+    """dpf_cpp.gen(k, n, seed, prf) with the same first 4 seed bytes reproduces the
+    reference's keys bit for bit (dpf_wrapper.cu:52 seeds mt19937 from them)."""
+    import dpf_cpp
+    for ci in (0, 9, 18, 27):
+        prf, n, alpha, seed32 = [int(v) for v in golden["case_meta"][ci]]
+        seed = seed32.to_bytes(4, "little") + b"\x00" * 124
+        k1, k2 = dpf_cpp.gen(alpha, n, seed, prf)
+        assert np.array_equal(k1.numpy(), golden["keys_a"][ci])
+        assert np.array_equal(k2.numpy(), golden["keys_b"][ci])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/dpf.py"), reason="reference tree only exists in the build container")
+def test_reference_dpf_py_runs_on_our_extension():
+    """The reference's own dpf.py, unmodified, imports our dpf_cpp and passes its CPU self-test."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_dpf", "/root/reference/dpf.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.test_cpu_dpf_one_hot()
+    assert repr(mod.DPF()) == "DPF(_uninitialized_, prf_method=AES128)"
