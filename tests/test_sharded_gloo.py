@@ -1,0 +1,83 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 (and 4) process groups over
+gloo.  The per-rank partial is supplied by the oracle (a test stand-in injected through
+ShardedDPF's partial_fn hook); what is under test is the product's shard index math,
+process-group plumbing and the int32 wrapping reduce."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, prf, ret):
+    for sub in ("gpu-dpf_b200", "oracle", "tests"):
+        sys.path.insert(0, os.path.join(ROOT, sub))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from common import random_table, seeded_keys
+    from sharded import ShardedDPF, shard_indices
+    orc = O.Oracle()
+    table = random_table(n, 16, seed=3)
+    ka, kb, idx = seeded_keys(orc.gen, n, 6, prf, seed=5)
+
+    # the rows this rank would upload, in device order, must be exactly the oracle's shard
+    rows = shard_indices(n, rank, world)
+    depth = n.bit_length() - 1
+    assert rows == [orc.bitrev(rank * (n // world) + q, depth) for q in range(n // world)]
+
+    def partial(packed):
+        out = np.stack([orc.eval_dot_shard(k, prf, table, rank * (n // world), n // world) for k in packed.numpy()])
+        return torch.from_numpy(out)
+
+    d = ShardedDPF(prf=prf, partial_fn=partial)
+    d.eval_init(torch.from_numpy(table))
+    got_a = d.eval_gpu([torch.from_numpy(k) for k in ka])
+    got_b = d.eval_gpu(torch.from_numpy(kb))
+    if rank == 0:
+        assert np.array_equal(got_a.numpy(), orc.eval_dot(ka, prf, table))
+        rec = (got_a.numpy().astype(np.uint32) - got_b.numpy().astype(np.uint32)).astype(np.int32)
+        assert np.array_equal(rec, table[idx])
+        ret.put("ok")
+    else:
+        assert got_a is None and got_b is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_reduce_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 1024, 2, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert ret.get(timeout=5) == "ok"
+
+
+def test_shard_indices_partition():
+    sys.path.insert(0, os.path.join(ROOT, "gpu-dpf_b200"))
+    from sharded import shard_indices
+    n = 256
+    for world in (1, 2, 8):
+        seen = sorted(i for r in range(world) for i in shard_indices(n, r, world))
+        assert seen == list(range(n))
+    # residue class of the LOW bits: the root of the tree consumes the index LSB
+    assert all(i % 4 == 0b10 for i in shard_indices(n, 1, 4))
