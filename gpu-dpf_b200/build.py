@@ -53,7 +53,8 @@ def _stale(target, deps):
 def build_lib(force=False, verbose=False):
     if not force and not _stale(LIB, LIB_DEPS):
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+    extra = os.environ.get("B200DPF_EXTRA_NVCC_FLAGS", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [
         "-shared", "-I", INCLUDE, "-o", LIB] + [os.path.join(CSRC, s) for s in LIB_SOURCES]
     subprocess.run(cmd, check=True)
     return LIB

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -72,7 +73,7 @@ struct b200dpf_ctx {
     int64_t n = 0;
     int depth = 0;
     int entry_size = 0;
-    int entry_pad = 0;       /* entry size rounded up to 16 int32 (64-byte rows) */
+    int entry_pad = 0;       /* row length in int32: 16, 32 or a multiple of 64     */
     int shard_rank = 0, shard_count = 1, shard_bits = 0;
     int64_t n_local = 0;
     int depth_local = 0;
@@ -83,7 +84,9 @@ struct b200dpf_ctx {
     int32_t *d_out = nullptr;
     size_t out_cap = 0;      /* int32 elements */
     uint32_t *d_counters = nullptr;
-    size_t counters_cap = 0;
+    size_t counters_cap = 0;  /* bytes */
+    void *d_frontier = nullptr;
+    size_t frontier_cap = 0;  /* bytes */
     int sm_count = 0;
     uint32_t smem_base = 0;
     int s_override = 0;
@@ -92,34 +95,31 @@ struct b200dpf_ctx {
 
 namespace {
 
-struct LaunchPlan {
-    EvalParams p;
-    int grid;
-    size_t smem;
+struct SmemLayout {
+    int threads, blocks_per_sm, grid;
+    size_t smem_fixed;        /* AES: whole budget; others: computed from s */
+    uint32_t off_meta, off_lo, off_hi, off_tab, meta_cw, level_bytes;
+    int cap_lo, cap_hi, s_max;
 };
 
-/* Decide subtree size, grid and the dynamic shared memory layout. */
-int plan_launch(b200dpf_ctx *c, int prf, int mode, int64_t nkeys, LaunchPlan *plan)
+/* Dynamic shared memory layout of the kernel instantiated for (prf, nv, mode). */
+int smem_layout(b200dpf_ctx *c, int prf, int nv, int mode, SmemLayout *L)
 {
-    EvalParams &p = plan->p;
-    std::memset(&p, 0, sizeof p);
-    const int threads = eval_threads(prf);
-    const int blocks_per_sm = eval_min_blocks(prf);
+    std::memset(L, 0, sizeof *L);
+    L->threads = eval_threads(prf, nv);
+    L->blocks_per_sm = eval_min_blocks(prf, nv);
+    L->grid = c->sm_count * L->blocks_per_sm;
     int max_smem = 0;
-    CUDA_TRY(eval_max_smem(prf, mode, &max_smem));
+    CUDA_TRY(eval_max_smem(prf, nv, mode, &max_smem));
     int sm_total = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
     /* every resident block also pays the 1 KiB system reservation */
-    int budget = std::min(max_smem, sm_total / blocks_per_sm - 1024);
+    int budget = std::min(max_smem, sm_total / L->blocks_per_sm - 1024);
     budget &= ~15;
 
-    const uint32_t meta_cw = (uint32_t)c->depth * 4u * 32u * 16u;
-    const uint32_t meta = meta_cw + 512u + 512u + 16u;
-    const uint32_t level_bytes = (uint32_t)threads * 16u;
-
-    int s_max;
-    uint32_t off_meta, off_lo, off_hi;
-    int cap_lo, cap_hi;   /* stack levels that fit in each region */
+    L->meta_cw = (uint32_t)c->depth * 4u * 32u * 16u;
+    const uint32_t meta = L->meta_cw + 512u + 512u + 16u;
+    L->level_bytes = (uint32_t)L->threads * 16u;
     if (prf == B200DPF_PRF_AES128) {
         /* tables: 128 KiB whose shared-window address is 64 KiB aligned */
         const uint32_t tab_abs = (c->smem_base + 65535u) & ~65535u;
@@ -128,99 +128,188 @@ int plan_launch(b200dpf_ctx *c, int prf, int mode, int64_t nkeys, LaunchPlan *pl
         const uint32_t b_off = off_tab + 131072u;                /* region B: after them        */
         if ((int64_t)budget < (int64_t)b_off) return fail(B200DPF_ECUDA, "shared memory too small for AES tables");
         const uint32_t b_size = (uint32_t)budget - b_off;
-        p.off_tab = off_tab;
+        L->off_tab = off_tab;
         uint32_t a_used = 0, b_used = 0;
-        if (meta <= a_size) { off_meta = 0; a_used = meta; }
-        else if (meta <= b_size) { off_meta = b_off; b_used = meta; }
+        if (meta <= a_size) { L->off_meta = 0; a_used = meta; }
+        else if (meta <= b_size) { L->off_meta = b_off; b_used = meta; }
         else return fail(B200DPF_EINVAL, "depth %d needs more shared memory than available", c->depth);
         a_used = (a_used + 15u) & ~15u;
         b_used = (b_used + 15u) & ~15u;
-        off_lo = b_off + b_used;
-        cap_lo = (int)((b_size - b_used) / level_bytes);
-        off_hi = a_used;
-        cap_hi = (int)((a_size - a_used) / level_bytes);
-        plan->smem = (size_t)budget;
+        L->off_lo = b_off + b_used;
+        L->cap_lo = (int)((b_size - b_used) / L->level_bytes);
+        L->off_hi = a_used;
+        L->cap_hi = (int)((a_size - a_used) / L->level_bytes);
+        L->smem_fixed = (size_t)budget;
     } else {
-        off_meta = 0;
-        off_lo = (meta + 15u) & ~15u;
-        if ((int64_t)budget < (int64_t)off_lo) return fail(B200DPF_EINVAL, "depth %d needs more shared memory than available", c->depth);
-        cap_lo = (int)(((uint32_t)budget - off_lo) / level_bytes);
-        off_hi = off_lo;
-        cap_hi = 0;
-        plan->smem = 0;   /* set below once s is known */
+        L->off_meta = 0;
+        L->off_lo = (meta + 15u) & ~15u;
+        if ((int64_t)budget < (int64_t)L->off_lo) return fail(B200DPF_EINVAL, "depth %d needs more shared memory than available", c->depth);
+        L->cap_lo = (int)(((uint32_t)budget - L->off_lo) / L->level_bytes);
+        L->off_hi = L->off_lo;
+        L->cap_hi = 0;
+        L->smem_fixed = 0;
     }
-    s_max = 1 + cap_lo + cap_hi;
-
-    plan->grid = c->sm_count * blocks_per_sm;
-    const int64_t key_groups = (nkeys + 31) / 32;
-    const int64_t warps = (int64_t)plan->grid * (threads / 32);
-
-    int s = std::min(c->depth_local, std::min(s_max, 10));
-    if (c->s_override > 0) {
-        s = std::min(c->s_override, std::min(c->depth_local, s_max));
-    } else {
-        /* enough work items for every resident warp to draw several */
-        while (s > 5 && (((int64_t)1 << (c->depth_local - s)) * key_groups) < 6 * warps) s--;
-    }
-    if (s < 1) s = 1;
-
-    p.depth = c->depth;
-    p.s = s;
-    p.nsub = (uint32_t)1 << (c->depth_local - s);
-    p.sub_first = (uint32_t)c->shard_rank << (c->depth_local - s);
-    p.nkeys = (int)nkeys;
-    p.key_groups = (int)key_groups;
-    p.table = reinterpret_cast<const uint4 *>(c->d_table);
-    p.row_stride_v = (uint32_t)c->entry_pad / 4u;
-    p.out_stride = (uint32_t)c->entry_size;
-    p.n = (uint64_t)c->n;
-    p.off_cw = off_meta;
-    p.off_cwlo = off_meta + meta_cw;
-    p.off_root = p.off_cwlo + 512u;
-    p.off_flag = p.off_root + 512u;
-    p.off_stack_lo = off_lo;
-    p.off_stack_hi = off_hi;
-    p.stack_split = std::min(cap_lo, s - 1);
-    if (prf != B200DPF_PRF_AES128) plan->smem = (size_t)off_lo + (size_t)(s > 1 ? s - 1 : 0) * level_bytes;
-    if (plan->grid > (int)(key_groups * p.nsub * 1)) {
-        /* fewer work items than blocks: still fine, idle blocks exit quickly */
-    }
+    L->s_max = 1 + L->cap_lo + L->cap_hi;
     return B200DPF_OK;
 }
 
-int ensure_counters(b200dpf_ctx *c, size_t count)
+void fill_common(const b200dpf_ctx *c, const SmemLayout &L, int s, int64_t nkeys, EvalParams *p, size_t *smem)
 {
-    if (count <= c->counters_cap) return B200DPF_OK;
-    if (c->d_counters) cudaFree(c->d_counters);
-    c->d_counters = nullptr;
-    c->counters_cap = 0;
-    CUDA_TRY(cudaMalloc(&c->d_counters, count * sizeof(uint32_t)));
-    c->counters_cap = count;
+    std::memset(p, 0, sizeof *p);
+    p->depth = c->depth;
+    p->s = s;
+    p->nkeys = (int)nkeys;
+    p->key_groups = (int)((nkeys + 31) / 32);
+    p->table = reinterpret_cast<const uint4 *>(c->d_table);
+    p->row_stride_v = (uint32_t)c->entry_pad / 4u;
+    p->out_stride = (uint32_t)c->entry_size;
+    p->n = (uint64_t)c->n;
+    p->off_cw = L.off_meta;
+    p->off_cwlo = L.off_meta + L.meta_cw;
+    p->off_root = p->off_cwlo + 512u;
+    p->off_flag = p->off_root + 512u;
+    p->off_stack_lo = L.off_lo;
+    p->off_stack_hi = L.off_hi;
+    p->stack_split = std::min(L.cap_lo, s - 1);
+    p->off_tab = L.off_tab;
+    *smem = L.smem_fixed ? L.smem_fixed : (size_t)L.off_lo + (size_t)(s > 1 ? s - 1 : 0) * L.level_bytes;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+int ensure_buffer(void **ptr, size_t *cap, size_t bytes)
+{
+    if (bytes <= *cap) return B200DPF_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    CUDA_TRY(cudaMalloc(ptr, bytes));
+    *cap = bytes;
+    return B200DPF_OK;
+}
+
+/*
+ * The launch pipeline of one evaluation:
+ *   [memset tickets (+ out)]  ->  [frontier kernel]  ->  main kernel x passes
+ * mode_main is MODE_FUSED (out = [nkeys][entry_size] int32) or MODE_EXPAND
+ * (out = [nkeys][n] int32 share vectors).
+ */
+int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, int mode_main, void *out_dev,
+                 cudaStream_t stream)
+{
+    const int nv = (mode_main != MODE_FUSED || c->entry_pad <= 16) ? 4 : (c->entry_pad <= 32 ? 8 : 16);
+    const int passes = mode_main == MODE_FUSED ? c->entry_pad / (4 * nv) : 1;
+    SmemLayout L;
+    int rc = smem_layout(c, prf, nv, mode_main, &L);
+    if (rc) return rc;
+    const int64_t key_groups = (nkeys + 31) / 32;
+    const int64_t warps = (int64_t)L.grid * (L.threads / 32);
+
+    /* ---- work-item size s and the frontier depth --------------------------------
+     * measured on B200 (profiles/r1_sweeps.txt).  Without a frontier every item
+     * re-walks depth-s levels from the root, so items must be big; with one the
+     * walk is (almost) free and small items balance the tail. */
+    const bool want_frontier = env_int("B200DPF_FRONTIER", 1) != 0;
+    const int s_env = c->s_override > 0 ? c->s_override : env_int("B200DPF_S", 0);
+    int s;
+    if (s_env > 0) {
+        s = std::min(s_env, std::min(c->depth_local, L.s_max));
+    } else {
+        /* B=512 E=16 1xB200, DPFs/s (profiles/r1_sweeps.txt):
+         *   AES n=2^20, frontier: s=4 23.99k, 5 24.83k, 6 25.03k, 7 25.01k, 8 24.92k; no frontier s=8 24.19k
+         *   AES n=2^16, frontier: s=4 372.7k, 5 366.4k, 6 351.7k; no frontier 340.3k
+         *   AES n=2^14, frontier: s=3 1.242M, 4 1.179M, 5 1.147M; no frontier 1.225M
+         *   ChaCha n=2^20, frontier: s=5 22.93k, 6 23.20k, 7 23.30k, 8 23.23k; no frontier 22.10k */
+        const int s_cap = want_frontier ? 7 : ((prf == B200DPF_PRF_AES128) ? 8 : 10);
+        const int s_floor = want_frontier ? 3 : 5;
+        const int64_t items_per_warp = want_frontier ? 24 : 6;
+        s = std::min(c->depth_local, std::min(L.s_max, s_cap));
+        while (s > s_floor && (((int64_t)1 << (c->depth_local - s)) * key_groups) < items_per_warp * warps) s--;
+    }
+    if (s < 1) s = 1;
+    const int rel = c->depth_local - s;           /* tree levels between the shard root and the items */
+
+    int f_rel = 0;                                /* frontier depth below the shard root (0 = none) */
+    if (want_frontier && rel >= 2) {
+        const int64_t cap_bytes = (int64_t)env_int("B200DPF_FRONTIER_MB", 256) << 20;
+        f_rel = rel;
+        while (f_rel > 0 && ((key_groups * 512) << f_rel) > cap_bytes) f_rel--;
+        if (f_rel < 2) f_rel = 0;
+    }
+
+    const size_t n_counters = (size_t)(passes + 1) * (size_t)key_groups;
+    rc = ensure_buffer(reinterpret_cast<void **>(&c->d_counters), &c->counters_cap, n_counters * sizeof(uint32_t));
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, n_counters * sizeof(uint32_t), stream));
+    if (mode_main == MODE_FUSED)
+        CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)nkeys * c->entry_size * sizeof(int32_t), stream));
+    c->last_launches = 0;
+
+    EvalParams p;
+    size_t smem;
+    if (f_rel > 0) {
+        rc = ensure_buffer(reinterpret_cast<void **>(&c->d_frontier), &c->frontier_cap,
+                           ((size_t)key_groups * 512) << f_rel);
+        if (rc) return rc;
+        SmemLayout LF;
+        rc = smem_layout(c, prf, 4, MODE_FRONTIER, &LF);
+        if (rc) return rc;
+        const int s_top = std::min(f_rel, std::min(5, LF.s_max));
+        fill_common(c, LF, s_top, nkeys, &p, &smem);
+        p.keys = reinterpret_cast<const uint4 *>(keys_dev);
+        p.nsub = (uint32_t)1 << (f_rel - s_top);
+        p.sub_first = (uint32_t)c->shard_rank << (f_rel - s_top);
+        p.walk_first_level = c->depth - 1;
+        p.walk_steps = c->shard_bits + f_rel - s_top;
+        p.level_base = c->depth_local - f_rel;
+        p.nfront = (uint32_t)1 << f_rel;
+        p.frontier_out = reinterpret_cast<uint4 *>(c->d_frontier);
+        p.counters = c->d_counters + (size_t)passes * key_groups;
+        CUDA_TRY(launch_eval(prf, 4, MODE_FRONTIER, p, LF.grid, smem, stream));
+        c->last_launches++;
+    }
+
+    fill_common(c, L, s, nkeys, &p, &smem);
+    p.keys = reinterpret_cast<const uint4 *>(keys_dev);
+    p.nsub = (uint32_t)1 << rel;
+    p.sub_first = (uint32_t)c->shard_rank << rel;
+    if (f_rel > 0) {
+        p.frontier_in = reinterpret_cast<const uint4 *>(c->d_frontier);
+        p.nfront = (uint32_t)1 << f_rel;
+        p.front_shift = rel - f_rel;
+        p.walk_first_level = c->depth_local - f_rel - 1;
+        p.walk_steps = rel - f_rel;
+    } else {
+        p.walk_first_level = c->depth - 1;
+        p.walk_steps = c->depth - s;
+    }
+    if (mode_main == MODE_EXPAND) {
+        p.shares = reinterpret_cast<uint32_t *>(out_dev);
+        p.counters = c->d_counters;
+        CUDA_TRY(launch_eval(prf, 4, MODE_EXPAND, p, L.grid, smem, stream));
+        c->last_launches++;
+        return B200DPF_OK;
+    }
+    p.out = reinterpret_cast<uint32_t *>(out_dev);
+    for (int pass = 0; pass < passes; pass++) {
+        p.col_off_v = (uint32_t)(pass * nv);
+        p.col_off = (uint32_t)(pass * 4 * nv);
+        p.ncols = (uint32_t)std::max(0, std::min(4 * nv, c->entry_size - pass * 4 * nv));
+        if (p.ncols == 0) break;
+        p.counters = c->d_counters + (size_t)pass * key_groups;
+        CUDA_TRY(launch_eval(prf, nv, MODE_FUSED, p, L.grid, smem, stream));
+        c->last_launches++;
+    }
     return B200DPF_OK;
 }
 
 int run_eval(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *out_dev, cudaStream_t stream)
 {
-    LaunchPlan plan;
-    int rc = plan_launch(c, prf, 0, nkeys, &plan);
-    if (rc) return rc;
-    const int passes = c->entry_pad / 16;
-    rc = ensure_counters(c, (size_t)passes * (size_t)plan.p.key_groups);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, (size_t)passes * plan.p.key_groups * sizeof(uint32_t), stream));
-    CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)nkeys * c->entry_size * sizeof(int32_t), stream));
-    plan.p.keys = reinterpret_cast<const uint4 *>(keys_dev);
-    plan.p.out = reinterpret_cast<uint32_t *>(out_dev);
-    c->last_launches = 0;
-    for (int pass = 0; pass < passes; pass++) {
-        plan.p.col_off_v = (uint32_t)pass * 4u;
-        plan.p.col_off = (uint32_t)pass * 16u;
-        plan.p.ncols = (uint32_t)std::min(16, c->entry_size - pass * 16);
-        plan.p.counters = c->d_counters + (size_t)pass * plan.p.key_groups;
-        CUDA_TRY(launch_eval(prf, 0, plan.p, plan.grid, plan.smem, stream));
-        c->last_launches++;
-    }
-    return B200DPF_OK;
+    return run_pipeline(c, keys_dev, nkeys, prf, MODE_FUSED, out_dev, stream);
 }
 
 int check_eval_args(const b200dpf_ctx *c, const void *keys, int64_t nkeys, int prf, const void *out)
@@ -310,7 +399,8 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     c->n = n;
     c->depth = ilog2(n);
     c->entry_size = entry_size;
-    c->entry_pad = (entry_size + 15) & ~15;
+    /* rows padded to what one pass reads: 16, 32 or a multiple of 64 int32 */
+    c->entry_pad = entry_size <= 16 ? 16 : (entry_size <= 32 ? 32 : ((entry_size + 63) & ~63));
     c->shard_rank = shard_rank;
     c->shard_count = shard_count;
     c->shard_bits = ilog2(shard_count);
@@ -384,6 +474,7 @@ int b200dpf_destroy(b200dpf_ctx *c)
     if (c->d_keys) cudaFree(c->d_keys);
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_frontier) cudaFree(c->d_frontier);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B200DPF_OK;
@@ -439,19 +530,7 @@ int b200dpf_expand_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, i
     if (c->shard_count != 1) return fail(B200DPF_ESTATE, "expand needs an unsharded context");
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
-    LaunchPlan plan;
-    rc = plan_launch(c, prf, 1, nkeys, &plan);
-    if (rc) return rc;
-    rc = ensure_counters(c, (size_t)plan.p.key_groups);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, (size_t)plan.p.key_groups * sizeof(uint32_t), stream));
-    plan.p.keys = reinterpret_cast<const uint4 *>(keys_dev);
-    plan.p.shares = reinterpret_cast<uint32_t *>(shares_dev);
-    plan.p.counters = c->d_counters;
-    CUDA_TRY(launch_eval(prf, 1, plan.p, plan.grid, plan.smem, stream));
-    c->last_launches = 1;
-    return B200DPF_OK;
+    return run_pipeline(c, keys_dev, nkeys, prf, MODE_EXPAND, shares_dev, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 int64_t b200dpf_ctx_n(const b200dpf_ctx *c) { return c ? c->n : -1; }

@@ -67,6 +67,33 @@ DPF_HD uint32_t rotl(uint32_t v, int r)
 #endif
 }
 
+/* Rotate through the FMA pipe: x*2^r as a 64-bit product has the rotated word
+ * split across its halves (low = x<<r, high = x>>(32-r)), which do not overlap.
+ * One IMAD.WIDE + one add, no ALU-pipe slot: used for a fraction of the
+ * Salsa/ChaCha rotates because those kernels saturate the ALU pipe (LOP3/SHF)
+ * while the FMA pipe idles (profiles/r1_ncu_full_chacha20_*). */
+#ifndef DPF_FMA_ROT_MASK
+#define DPF_FMA_ROT_MASK 0
+#endif
+template <int R>
+DPF_HD uint32_t rotl_fma(uint32_t v)
+{
+#if DPF_DEVICE_CODE
+    uint32_t lo, hi;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0,%1}, t;\n\t}"
+        : "=r"(lo), "=r"(hi) : "r"(v), "n"(1u << R));
+    return lo + hi;
+#else
+    return (v << R) | (v >> (32 - R));
+#endif
+}
+/* rotate number `SLOT` (0..3) of a quarter round: FMA pipe if its mask bit is set */
+template <int SLOT, int R>
+DPF_HD uint32_t rot_sel(uint32_t v)
+{
+    return ((DPF_FMA_ROT_MASK >> SLOT) & 1) ? rotl_fma<R>(v) : rotl(v, R);
+}
+
 /* PRMT: pick 4 bytes out of the 8 bytes {a (0-3), b (4-7)}; selector nibbles
  * 0-7 only (no sign replication), least significant nibble -> byte 0. */
 DPF_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
@@ -130,18 +157,18 @@ DPF_HD Seed dummy_prf(const Seed &s, uint32_t pos)
 
 #define DPF_SALSA_QR(a, b, c, d)      \
     do {                              \
-        b ^= rotl(a + d, 7);          \
-        c ^= rotl(b + a, 9);          \
-        d ^= rotl(c + b, 13);         \
-        a ^= rotl(d + c, 18);         \
+        b ^= rot_sel<0, 7>(a + d);    \
+        c ^= rot_sel<1, 9>(b + a);    \
+        d ^= rot_sel<2, 13>(c + b);   \
+        a ^= rot_sel<3, 18>(d + c);   \
     } while (0)
 
 #define DPF_CHACHA_QR(a, b, c, d)     \
     do {                              \
-        a += b; d = rotl(d ^ a, 16);  \
-        c += d; b = rotl(b ^ c, 12);  \
-        a += b; d = rotl(d ^ a, 8);   \
-        c += d; b = rotl(b ^ c, 7);   \
+        a += b; d = rot_sel<0, 16>(d ^ a);  \
+        c += d; b = rot_sel<1, 12>(b ^ c);  \
+        a += b; d = rot_sel<2, 8>(d ^ a);   \
+        c += d; b = rot_sel<3, 7>(b ^ c);   \
     } while (0)
 
 /*
@@ -373,20 +400,24 @@ DPF_HD Seed expand_one(const TA &ta, const Seed &parent, uint32_t pos)
  *     Seed     cw(level, bank, bit)      correction word
  *     uint32_t cw_lo(bank, bit)          low word of the level-0 correction word
  *     void     push(h, Seed), Seed pop(h) pending right child of height h
+ *     void     leaf_prefetch(local_pos)      called before the leaf pair is expanded
  *     void     leaf_pair(local_pos, v0, v1)  consume leaves local_pos, local_pos+1
+ *     void     node_pair(local_pos, c0, c1)  (FULL mode) consume whole seeds
  *     ta                                 AES table policy
  */
 
-/* Walk from the root of the key to the root of subtree `q` (breadth-first index
- * among the 2^(depth-s) nodes at that depth).  `q` is the same for every lane of
- * a warp, so the branch bits are uniform. */
+/* Walk `steps` levels down from `seed`, whose children are produced with
+ * correction-word level `first_level`; the branch taken at step k is bit
+ * (steps-1-k) of `q`.  From the key's root (first_level = depth-1) with
+ * steps = depth-s this reaches the root of the 2^s-leaf subtree with
+ * breadth-first index q.  `q` is the same for every lane of a warp, so the
+ * branch bits are warp-uniform. */
 template <int PRF, class Env>
-DPF_HD Seed walk_to_subtree(Env &env, Seed seed, int depth, int s, uint32_t q)
+DPF_HD Seed walk_down(Env &env, Seed seed, int first_level, int steps, uint32_t q)
 {
-    const int steps = depth - s;
     for (int k = 0; k < steps; k++) {
         const uint32_t bit = (q >> (steps - 1 - k)) & 1u;
-        const int level = depth - 1 - k;
+        const int level = first_level - k;
         const uint32_t bank = seed.x & 1u;
         seed = add128(expand_one<PRF>(env.ta, seed, bit), env.cw(level, bank, bit));
     }
@@ -404,12 +435,19 @@ DPF_HD int ctz32(uint32_t v)
 
 /*
  * Depth-first expansion of a complete subtree with 2^s leaves, one node pair at
- * a time, keeping only the pending right siblings (one per height).  Heights:
- * a node of height h has 2^h leaves below it; expanding it uses level h-1.
- * Leaves are produced in increasing position order, two per step.
+ * a time, keeping only the pending right siblings (one per height).  A node of
+ * height h has 2^h leaves below it; expanding it uses correction-word level
+ * level_base + h - 1 (level_base = 0 when the subtree's leaves are the leaves
+ * of the whole tree).  Leaves come out in increasing position order, two per
+ * step:
+ *   FULL = false: only their low 32 bits (the fused inner product / share
+ *                 vector needs nothing else, dpf_wrapper.cu:182) via
+ *                 env.leaf_pair(local_pos, v0, v1); requires level_base == 0;
+ *   FULL = true : whole 128-bit seeds via env.node_pair(local_pos, c0, c1) --
+ *                 used to materialise an interior frontier of the tree.
  */
-template <int PRF, class Env>
-DPF_HD void eval_subtree(Env &env, Seed seed, int s)
+template <int PRF, bool FULL, class Env>
+DPF_HD void eval_subtree(Env &env, Seed seed, int s, int level_base)
 {
     int h = s;
     const uint32_t npairs = 1u << (s - 1);
@@ -418,16 +456,22 @@ DPF_HD void eval_subtree(Env &env, Seed seed, int s)
             Seed c0, c1;
             expand_pair<PRF, false>(env.ta, seed, c0, c1);
             const uint32_t bank = seed.x & 1u;
-            c1 = add128(c1, env.cw(h - 1, bank, 1));
+            const int level = level_base + h - 1;
+            c1 = add128(c1, env.cw(level, bank, 1));
             env.push(h - 1, c1);
-            seed = add128(c0, env.cw(h - 1, bank, 0));
+            seed = add128(c0, env.cw(level, bank, 0));
             h--;
         }
         Seed l0, l1;
-        env.leaf_prefetch(2 * i);
-        expand_pair<PRF, true>(env.ta, seed, l0, l1);
         const uint32_t bank = seed.x & 1u;
-        env.leaf_pair(2 * i, l0.x + env.cw_lo(bank, 0), l1.x + env.cw_lo(bank, 1));
+        if (FULL) {
+            expand_pair<PRF, false>(env.ta, seed, l0, l1);
+            env.node_pair(2 * i, add128(l0, env.cw(level_base, bank, 0)), add128(l1, env.cw(level_base, bank, 1)));
+        } else {
+            env.leaf_prefetch(2 * i);
+            expand_pair<PRF, true>(env.ta, seed, l0, l1);
+            env.leaf_pair(2 * i, l0.x + env.cw_lo(bank, 0), l1.x + env.cw_lo(bank, 1));
+        }
         h = ctz32(i + 1) + 1;
         if (h < s) seed = env.pop(h);
     }

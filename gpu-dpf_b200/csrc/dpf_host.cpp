@@ -227,6 +227,7 @@ struct CpuEnv {
     void push(int h, const Seed &s) { stack[h] = s; }
     Seed pop(int h) const { return stack[h]; }
     void leaf_prefetch(uint32_t) {}
+    void node_pair(uint32_t, const Seed &, const Seed &) {}
     static uint32_t bitrev(uint32_t v, int bits)
     {
         uint32_t r = 0;
@@ -254,8 +255,8 @@ void eval_cpu_impl(const int32_t *key, int depth, int32_t *out)
     const uint32_t nsub = 1u << (depth - s);
     for (uint32_t q = 0; q < nsub; q++) {
         env.base_pos = q << s;
-        const Seed r = walk_to_subtree<PRF>(env, key_slot(key, SLOT_ROOT), depth, s, q);
-        eval_subtree<PRF>(env, r, s);
+        const Seed r = walk_down<PRF>(env, key_slot(key, SLOT_ROOT), depth - 1, depth - s, q);
+        eval_subtree<PRF, false>(env, r, s, 0);
     }
 }
 

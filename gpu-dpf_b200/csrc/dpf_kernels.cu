@@ -30,6 +30,14 @@
  *                 so lookups are conflict-free, and the shared address of a
  *                 lookup is formed by ONE PRMT (byte insert into a 64 KiB-aligned
  *                 base) + the LDS immediate offset.
+ *   frontier    = an optional first launch (MODE_FRONTIER) expands the top of every
+ *                 key's tree once and stores the seeds of all depth-F nodes; the
+ *                 main launch then starts each work item from its frontier node
+ *                 instead of re-walking from the root, so work items can be small
+ *                 (good load balance) without paying a root-to-subtree walk each.
+ *   wide rows   = NV uint4 of a table row per pass (16/32/64 int32 columns): the
+ *                 first 64 bytes of both rows are prefetched before the leaf
+ *                 expansion, the rest streamed chunk by chunk during the MAC.
  *   scheduling  = persistent blocks; warps draw subtrees from a per-key-group
  *                 ticket counter (atomicAdd), blocks migrate to the next key
  *                 group when theirs runs dry, partial sums leave through
@@ -82,7 +90,8 @@ struct DevEnv {
     const uint4 *rows;          /* first row of the current subtree, at this pass's column */
     uint32_t row_stride_v;
     uint32_t acc[4 * NV];
-    uint4 ra[NV], rb[NV];
+    uint4 ra[4], rb[4];         /* prefetched first 64 bytes of the two rows of a leaf pair */
+    uint4 *front_out;           /* MODE_FRONTIER: &frontier[(kg*nfront + first node)*32 + lane] */
     /* expand mode */
     uint32_t *share_row;        /* shares + key*n */
     uint32_t pos_base;          /* global leaf position of the subtree's first leaf */
@@ -114,43 +123,67 @@ struct DevEnv {
     }
     __device__ __forceinline__ void leaf_prefetch(uint32_t local_pos)
     {
-        if (MODE == 0) {
+        if (MODE == MODE_FUSED) {
             const uint4 *r = rows + (size_t)local_pos * row_stride_v;
 #pragma unroll
-            for (int j = 0; j < NV; j++) ra[j] = __ldg(r + j);
+            for (int j = 0; j < 4; j++) ra[j] = __ldg(r + j);
 #pragma unroll
-            for (int j = 0; j < NV; j++) rb[j] = __ldg(r + row_stride_v + j);
+            for (int j = 0; j < 4; j++) rb[j] = __ldg(r + row_stride_v + j);
         }
     }
     __device__ __forceinline__ void leaf_pair(uint32_t local_pos, uint32_t v0, uint32_t v1)
     {
-        if (MODE == 0) {
+        if (MODE == MODE_FUSED) {
+            const uint4 *r = rows + (size_t)local_pos * row_stride_v;
 #pragma unroll
-            for (int j = 0; j < NV; j++) {
-                acc[4 * j + 0] += v0 * ra[j].x + v1 * rb[j].x;
-                acc[4 * j + 1] += v0 * ra[j].y + v1 * rb[j].y;
-                acc[4 * j + 2] += v0 * ra[j].z + v1 * rb[j].z;
-                acc[4 * j + 3] += v0 * ra[j].w + v1 * rb[j].w;
+            for (int c = 0; c < NV / 4; c++) {
+                uint4 na[4], nb[4];
+                if (c + 1 < NV / 4) {   /* next 64 bytes of both rows while this chunk is multiplied */
+#pragma unroll
+                    for (int j = 0; j < 4; j++) na[j] = __ldg(r + 4 * (c + 1) + j);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) nb[j] = __ldg(r + row_stride_v + 4 * (c + 1) + j);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    acc[16 * c + 4 * j + 0] += v0 * ra[j].x + v1 * rb[j].x;
+                    acc[16 * c + 4 * j + 1] += v0 * ra[j].y + v1 * rb[j].y;
+                    acc[16 * c + 4 * j + 2] += v0 * ra[j].z + v1 * rb[j].z;
+                    acc[16 * c + 4 * j + 3] += v0 * ra[j].w + v1 * rb[j].w;
+                }
+                if (c + 1 < NV / 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { ra[j] = na[j]; rb[j] = nb[j]; }
+                }
             }
-        } else if (key_valid) {
+        } else if (MODE == MODE_EXPAND && key_valid) {
             /* leaf position p holds index bitrev_depth(p) */
             const uint32_t p = pos_base + local_pos;
             share_row[__brev(p) >> (32 - depth)] = v0;
             share_row[__brev(p + 1) >> (32 - depth)] = v1;
         }
     }
+    /* MODE_FRONTIER: whole seeds of two adjacent frontier nodes */
+    __device__ __forceinline__ void node_pair(uint32_t local_pos, const Seed &c0, const Seed &c1)
+    {
+        front_out[(size_t)local_pos * 32] = make_uint4(c0.x, c0.y, c0.z, c0.w);
+        front_out[(size_t)(local_pos + 1) * 32] = make_uint4(c1.x, c1.y, c1.z, c1.w);
+    }
 };
 
-template <int PRF> struct KernelShape { enum { THREADS = 256, MIN_BLOCKS = 2 }; };
-template <> struct KernelShape<PRF_AES128> { enum { THREADS = 384, MIN_BLOCKS = 1 }; };
+/* Block shape per (PRF, NV).  AES needs 128 KiB of the SM's shared memory for its
+ * tables, so one block per SM; accumulators (4*NV registers) decide how many
+ * threads fit the register file. */
+template <int PRF, int NV> struct KernelShape { enum { THREADS = (NV <= 8 ? 256 : 384), MIN_BLOCKS = (NV <= 8 ? 2 : 1) }; };
+template <int NV> struct KernelShape<PRF_AES128, NV> { enum { THREADS = (NV <= 8 ? 384 : 256), MIN_BLOCKS = 1 }; };
 
 extern __shared__ __align__(16) unsigned char g_dyn_smem[];
 
 template <int PRF, int NV, int MODE>
-__global__ void __launch_bounds__(KernelShape<PRF>::THREADS, KernelShape<PRF>::MIN_BLOCKS)
+__global__ void __launch_bounds__((KernelShape<PRF, NV>::THREADS), (KernelShape<PRF, NV>::MIN_BLOCKS))
 dpf_eval_kernel(const __grid_constant__ EvalParams p)
 {
-    constexpr int THREADS = KernelShape<PRF>::THREADS;
+    constexpr int THREADS = KernelShape<PRF, NV>::THREADS;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
@@ -215,10 +248,10 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
 
         const int key = kg * 32 + lane;
         env.key_valid = key < p.nkeys;
-        if (MODE == 0) {
+        if (MODE == MODE_FUSED) {
 #pragma unroll
             for (int e = 0; e < 4 * NV; e++) env.acc[e] = 0;
-        } else {
+        } else if (MODE == MODE_EXPAND) {
             env.share_row = p.shares + (size_t)(env.key_valid ? key : 0) * p.n;
         }
         const uint4 rv = root_s[lane];
@@ -229,13 +262,23 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
             if (lane == 0) q = atomicAdd(p.counters + kg, 1u);
             q = __shfl_sync(0xffffffffu, q, 0);
             if (q >= p.nsub) break;
-            env.rows = p.table + ((size_t)q << p.s) * p.row_stride_v + p.col_off_v;
-            env.pos_base = (p.sub_first + q) << p.s;
-            const Seed r = walk_to_subtree<PRF>(env, root, p.depth, p.s, p.sub_first + q);
-            eval_subtree<PRF>(env, r, p.s);
+            Seed start = root;
+            if (p.frontier_in != nullptr) {
+                const uint4 fv = p.frontier_in[((size_t)kg * p.nfront + (q >> p.front_shift)) * 32 + lane];
+                start = make_seed(fv.x, fv.y, fv.z, fv.w);
+            }
+            const Seed r = walk_down<PRF>(env, start, p.walk_first_level, p.walk_steps, p.sub_first + q);
+            if (MODE == MODE_FRONTIER) {
+                env.front_out = p.frontier_out + ((size_t)kg * p.nfront + ((size_t)q << p.s)) * 32 + lane;
+                eval_subtree<PRF, true>(env, r, p.s, p.level_base);
+            } else {
+                env.rows = p.table + ((size_t)q << p.s) * p.row_stride_v + p.col_off_v;
+                env.pos_base = (p.sub_first + q) << p.s;
+                eval_subtree<PRF, false>(env, r, p.s, 0);
+            }
         }
 
-        if (MODE == 0 && env.key_valid) {
+        if (MODE == MODE_FUSED && env.key_valid) {
             uint32_t *o = p.out + (size_t)key * p.out_stride + p.col_off;
 #pragma unroll
             for (int e = 0; e < 4 * NV; e++)
@@ -263,24 +306,24 @@ __global__ void permute_table_kernel(const int32_t *__restrict__ stage, int32_t 
     }
 }
 
-template <int PRF, int MODE>
+template <int PRF, int NV, int MODE>
 cudaError_t launch_one(const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
 {
-    auto kern = dpf_eval_kernel<PRF, 4, MODE>;
+    auto kern = dpf_eval_kernel<PRF, NV, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     /* the kernels live in shared memory; L1 only sees broadcast table rows */
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    kern<<<grid, KernelShape<PRF>::THREADS, smem, stream>>>(p);
+    kern<<<grid, (KernelShape<PRF, NV>::THREADS), smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-template <int PRF, int MODE>
+template <int PRF, int NV, int MODE>
 cudaError_t max_smem_one(int *bytes)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, dpf_eval_kernel<PRF, 4, MODE>);
+    cudaError_t e = cudaFuncGetAttributes(&a, dpf_eval_kernel<PRF, NV, MODE>);
     if (e != cudaSuccess) return e;
     int dev = 0, optin = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -289,10 +332,42 @@ cudaError_t max_smem_one(int *bytes)
     return cudaSuccess;
 }
 
+/* (prf, nv, mode) -> instantiation; modes 1 and 2 never touch the table, so NV = 4 only */
+template <int PRF>
+cudaError_t launch_prf(int nv, int mode, const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
+{
+    if (mode == MODE_EXPAND) return launch_one<PRF, 4, MODE_EXPAND>(p, grid, smem, stream);
+    if (mode == MODE_FRONTIER) return launch_one<PRF, 4, MODE_FRONTIER>(p, grid, smem, stream);
+    if (nv == 4) return launch_one<PRF, 4, MODE_FUSED>(p, grid, smem, stream);
+    if (nv == 8) return launch_one<PRF, 8, MODE_FUSED>(p, grid, smem, stream);
+    if (nv == 16) return launch_one<PRF, 16, MODE_FUSED>(p, grid, smem, stream);
+    return cudaErrorInvalidValue;
+}
+
+template <int PRF>
+cudaError_t max_smem_prf(int nv, int mode, int *bytes)
+{
+    if (mode == MODE_EXPAND) return max_smem_one<PRF, 4, MODE_EXPAND>(bytes);
+    if (mode == MODE_FRONTIER) return max_smem_one<PRF, 4, MODE_FRONTIER>(bytes);
+    if (nv == 4) return max_smem_one<PRF, 4, MODE_FUSED>(bytes);
+    if (nv == 8) return max_smem_one<PRF, 8, MODE_FUSED>(bytes);
+    if (nv == 16) return max_smem_one<PRF, 16, MODE_FUSED>(bytes);
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace
 
-int eval_threads(int prf) { return prf == PRF_AES128 ? (int)KernelShape<PRF_AES128>::THREADS : (int)KernelShape<PRF_DUMMY>::THREADS; }
-int eval_min_blocks(int prf) { return prf == PRF_AES128 ? (int)KernelShape<PRF_AES128>::MIN_BLOCKS : (int)KernelShape<PRF_DUMMY>::MIN_BLOCKS; }
+int eval_threads(int prf, int nv)
+{
+    if (prf == PRF_AES128) return nv <= 8 ? 384 : 256;
+    return nv <= 8 ? 256 : 384;
+}
+
+int eval_min_blocks(int prf, int nv)
+{
+    if (prf == PRF_AES128) return 1;
+    return nv <= 8 ? 2 : 1;
+}
 
 cudaError_t probe_dynamic_smem_base(uint32_t *base, cudaStream_t stream)
 {
@@ -312,34 +387,26 @@ cudaError_t upload_aes_table(const uint32_t *te0_256)
     return cudaMemcpyToSymbol(c_te0, te0_256, 256 * sizeof(uint32_t));
 }
 
-cudaError_t launch_eval(int prf, int mode, const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
+cudaError_t launch_eval(int prf, int nv, int mode, const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
 {
-#define DPF_DISPATCH(P)                                                     \
-    case P:                                                                 \
-        return mode == 0 ? launch_one<P, 0>(p, grid, smem, stream) : launch_one<P, 1>(p, grid, smem, stream);
     switch (prf) {
-        DPF_DISPATCH(PRF_DUMMY)
-        DPF_DISPATCH(PRF_SALSA20)
-        DPF_DISPATCH(PRF_CHACHA20)
-        DPF_DISPATCH(PRF_AES128)
+    case PRF_DUMMY: return launch_prf<PRF_DUMMY>(nv, mode, p, grid, smem, stream);
+    case PRF_SALSA20: return launch_prf<PRF_SALSA20>(nv, mode, p, grid, smem, stream);
+    case PRF_CHACHA20: return launch_prf<PRF_CHACHA20>(nv, mode, p, grid, smem, stream);
+    case PRF_AES128: return launch_prf<PRF_AES128>(nv, mode, p, grid, smem, stream);
     default: return cudaErrorInvalidValue;
     }
-#undef DPF_DISPATCH
 }
 
-cudaError_t eval_max_smem(int prf, int mode, int *bytes)
+cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes)
 {
-#define DPF_DISPATCH(P)                                                     \
-    case P:                                                                 \
-        return mode == 0 ? max_smem_one<P, 0>(bytes) : max_smem_one<P, 1>(bytes);
     switch (prf) {
-        DPF_DISPATCH(PRF_DUMMY)
-        DPF_DISPATCH(PRF_SALSA20)
-        DPF_DISPATCH(PRF_CHACHA20)
-        DPF_DISPATCH(PRF_AES128)
+    case PRF_DUMMY: return max_smem_prf<PRF_DUMMY>(nv, mode, bytes);
+    case PRF_SALSA20: return max_smem_prf<PRF_SALSA20>(nv, mode, bytes);
+    case PRF_CHACHA20: return max_smem_prf<PRF_CHACHA20>(nv, mode, bytes);
+    case PRF_AES128: return max_smem_prf<PRF_AES128>(nv, mode, bytes);
     default: return cudaErrorInvalidValue;
     }
-#undef DPF_DISPATCH
 }
 
 cudaError_t launch_permute_table(const int32_t *stage, int32_t *table, uint64_t rows, int bits,

@@ -23,6 +23,15 @@ struct EvalParams {
     uint32_t ncols;           /* valid int32 columns in this pass (<= 4*NV)             */
     int depth;                /* log2 n                                                 */
     int s;                    /* log2 leaves per work item (one warp = 32 keys x 2^s)   */
+    /* where a work item starts: the key's root seed, or a node of a precomputed
+     * frontier (seeds of every depth-F node of this shard, built by MODE 2)           */
+    const uint4 *frontier_in; /* [key_groups][nfront][32 keys] or null                  */
+    uint4 *frontier_out;      /* MODE 2 output, same layout                             */
+    uint32_t nfront;          /* frontier nodes per key (this shard)                    */
+    int front_shift;          /* work item q starts at frontier node q >> front_shift   */
+    int walk_first_level;     /* correction-word level of the first walk step           */
+    int walk_steps;           /* walk steps from the start node to the subtree root     */
+    int level_base;           /* level of the subtree's bottom expansion (0 = leaves)   */
     uint32_t sub_first;       /* breadth-first index of the shard's first 2^s-subtree   */
     uint32_t nsub;            /* number of 2^s-subtrees in this shard                   */
     uint32_t *counters;       /* [key_groups] work-item tickets, pre-zeroed             */
@@ -41,9 +50,14 @@ struct EvalParams {
                                  multiple of 64 KiB                                     */
 };
 
-/* Threads per block / minimum blocks per SM chosen for each PRF kernel. */
-int eval_threads(int prf);
-int eval_min_blocks(int prf);
+/* Kernel modes. */
+enum { MODE_FUSED = 0, MODE_EXPAND = 1, MODE_FRONTIER = 2 };
+
+/* Threads per block / minimum blocks per SM of the kernel instantiated for
+ * (prf, nv) where nv = uint4 (4 int32 columns) of a table row handled per pass:
+ * 4, 8 or 16. */
+int eval_threads(int prf, int nv);
+int eval_min_blocks(int prf, int nv);
 
 /* Shared-window address of the first dynamic shared memory byte (probed). */
 cudaError_t probe_dynamic_smem_base(uint32_t *base, cudaStream_t stream);
@@ -51,13 +65,14 @@ cudaError_t probe_dynamic_smem_base(uint32_t *base, cudaStream_t stream);
 /* Upload the AES T-table to this device's constant memory. */
 cudaError_t upload_aes_table(const uint32_t *te0_256);
 
-/* One pass of the fused evaluation (mode 0) or the share expansion (mode 1).
+/* One pass of the fused evaluation (mode 0), the share expansion (mode 1) or the
+ * frontier build (mode 2; nv must be 4 for modes 1 and 2).
  * grid = number of persistent blocks; smem_bytes = dynamic shared memory. */
-cudaError_t launch_eval(int prf, int mode, const EvalParams &p, int grid, size_t smem_bytes,
+cudaError_t launch_eval(int prf, int nv, int mode, const EvalParams &p, int grid, size_t smem_bytes,
                         cudaStream_t stream);
 
 /* Maximum dynamic shared memory the evaluation kernel may be given. */
-cudaError_t eval_max_smem(int prf, int mode, int *bytes);
+cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes);
 
 /* table[q][c] = stage[bitrev_bits(q)][c] for q < rows, c < cols; padded columns
  * [cols, stride) are left untouched (pre-zeroed). */
