@@ -293,29 +293,59 @@ DPF_HD void aes_round(const TA &ta, uint32_t &s0, uint32_t &s1, uint32_t &s2, ui
     s0 = t0; s1 = t1; s2 = t2; s3 = t3;
 }
 
+/*
+ * First cipher round fused with the first key-schedule step.  The state entering
+ * round 1 is plaintext ^ rk0 = (k0 ^ pos, k1, k2, k3), so the four lookups that
+ * index the bytes of column 3 (= k3) are the same S-box reads the key schedule
+ * needs for SubWord(RotWord(k3)): they are done once and their S bytes picked
+ * out with PRMTs (4 fewer lookups per node).  In: rk0 in k0..k3.  Out: rk1 in
+ * k0..k3, the state after round 1 in a0..a3, and in `col0_te0` the lookup
+ * Te0[byte 0 of column 0] (the only one the sibling with pos^1 does not share).
+ */
+template <class TA>
+DPF_HD void aes_first_round(const TA &ta, uint32_t pos, uint32_t &k0, uint32_t &k1, uint32_t &k2, uint32_t &k3,
+                            uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t &a3, uint32_t &col0_te0)
+{
+    const uint32_t s0 = k0 ^ pos;
+    const uint32_t l00 = ta.template te<0, 0>(s0), l11 = ta.template te<1, 1>(k1), l22 = ta.template te<2, 2>(k2), l33 = ta.template te<3, 3>(k3);
+    const uint32_t l01 = ta.template te<0, 0>(k1), l12 = ta.template te<1, 1>(k2), l23 = ta.template te<2, 2>(k3), l30 = ta.template te<3, 3>(s0);
+    const uint32_t l02 = ta.template te<0, 0>(k2), l13 = ta.template te<1, 1>(k3), l20 = ta.template te<2, 2>(s0), l31 = ta.template te<3, 3>(k1);
+    const uint32_t l03 = ta.template te<0, 0>(k3), l10 = ta.template te<1, 1>(s0), l21 = ta.template te<2, 2>(k1), l32 = ta.template te<3, 3>(k2);
+    /* SubWord(RotWord(k3)) = (S[b1], S[b2], S[b3], S[b0]) of k3:
+     *   l13 = Te1[b1] has S in bytes 2,3;  l23 = Te2[b2] in bytes 0,3;
+     *   l33 = Te3[b3] in bytes 0,1;        l03 = Te0[b0] in bytes 1,2 */
+    const uint32_t ab = prmt(l13, l23, 0x0042);   /* byte0 <- l13.2, byte1 <- l23.0 */
+    const uint32_t cd = prmt(l33, l03, 0x5000);   /* byte2 <- l33.0, byte3 <- l03.1 */
+    const uint32_t t = prmt(ab, cd, 0x7610);
+    k0 ^= t ^ 1u;
+    k1 ^= k0;
+    k2 ^= k1;
+    k3 ^= k2;
+    a0 = l00 ^ l11 ^ l22 ^ l33 ^ k0;
+    a1 = l01 ^ l12 ^ l23 ^ l30 ^ k1;
+    a2 = l02 ^ l13 ^ l20 ^ l31 ^ k2;
+    a3 = l03 ^ l10 ^ l21 ^ l32 ^ k3;
+    col0_te0 = l00;
+}
+
 /* Both children of one node: AES_seed(0) and AES_seed(1).  LEAF: .x only. */
 template <bool LEAF, class TA>
 DPF_HD void aes128_pair(const TA &ta, const Seed &s, Seed &c0, Seed &c1)
 {
     uint32_t k0 = s.x, k1 = s.y, k2 = s.z, k3 = s.w;
-    /* round 0: state = plaintext ^ rk0; plaintexts are 0 and 1 (byte 0) */
-    uint32_t a0 = k0, a1 = k1, a2 = k2, a3 = k3;
-    uint32_t b0 = k0 ^ 1u, b1 = k1, b2 = k2, b3 = k3;
-    uint32_t rc = 1;
+    uint32_t a0, a1, a2, a3, l00;
+    /* the children's plaintexts are 0 and 1: they differ in byte 0 of column 0,
+     * which after ShiftRows+MixColumns lands in output column 0 alone */
+    const uint32_t sib = ta.template te<0, 0>(k0 ^ 1u);
+    aes_first_round(ta, 0u, k0, k1, k2, k3, a0, a1, a2, a3, l00);
+    uint32_t b0 = a0 ^ l00 ^ sib, b1 = a1, b2 = a2, b3 = a3;
+    uint32_t rc = 2;
 DPF_UNROLL
-    for (int r = 1; r <= 9; r++) {
+    for (int r = 2; r <= 9; r++) {
         aes_next_rk(ta, k0, k1, k2, k3, rc);
         rc = (rc << 1) ^ ((rc & 0x80u) ? 0x11bu : 0u);
-        if (r == 1) {
-            /* children differ only in byte 0 of column 0, which after
-             * ShiftRows+MixColumns lands in output column 0 alone */
-            const uint32_t d = ta.template te<0, 0>(a0) ^ ta.template te<0, 0>(b0);
-            aes_round(ta, a0, a1, a2, a3, k0, k1, k2, k3);
-            b0 = a0 ^ d; b1 = a1; b2 = a2; b3 = a3;
-        } else {
-            aes_round(ta, a0, a1, a2, a3, k0, k1, k2, k3);
-            aes_round(ta, b0, b1, b2, b3, k0, k1, k2, k3);
-        }
+        aes_round(ta, a0, a1, a2, a3, k0, k1, k2, k3);
+        aes_round(ta, b0, b1, b2, b3, k0, k1, k2, k3);
     }
     aes_next_rk(ta, k0, k1, k2, k3, rc);
     /* final round: SubBytes + ShiftRows + AddRoundKey */
@@ -340,10 +370,11 @@ template <class TA>
 DPF_HD Seed aes128_one(const TA &ta, const Seed &s, uint32_t pos)
 {
     uint32_t k0 = s.x, k1 = s.y, k2 = s.z, k3 = s.w;
-    uint32_t a0 = k0 ^ pos, a1 = k1, a2 = k2, a3 = k3;
-    uint32_t rc = 1;
+    uint32_t a0, a1, a2, a3, l00;
+    aes_first_round(ta, pos, k0, k1, k2, k3, a0, a1, a2, a3, l00);
+    uint32_t rc = 2;
 DPF_UNROLL
-    for (int r = 1; r <= 9; r++) {
+    for (int r = 2; r <= 9; r++) {
         aes_next_rk(ta, k0, k1, k2, k3, rc);
         rc = (rc << 1) ^ ((rc & 0x80u) ? 0x11bu : 0u);
         aes_round(ta, a0, a1, a2, a3, k0, k1, k2, k3);
