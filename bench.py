@@ -40,19 +40,33 @@ BASELINE_PUBLISHED = {  # BASELINE.md section 1 (reference README.md:129-146), V
 }
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 20)
+    ap.add_argument("--entries", "--n", dest="n", type=int, default=1 << 20, help="table size n (use --entries under torchrun: --n is ambiguous to its parser)")
     ap.add_argument("--entry", type=int, default=16)
     ap.add_argument("--prf", default="aes128", choices=sorted(PRF_IDS))
     ap.add_argument("--batch-per-gpu", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--subtree-log2", type=int, default=0)
+    ap.add_argument("--reduce", default="nccl", choices=["nccl", "fused"],
+                    help="N>1: NCCL reduce of the partials, or the kernel's peer-memory red.add epilogue")
     return ap.parse_args()
 
 
@@ -197,7 +211,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "DPFs/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------
@@ -217,7 +231,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
 
     prf = PRF_IDS[args.prf]
@@ -227,7 +242,7 @@ def run_ours(args):
     keys_np, _ = synthetic_keys(n, batch, prf)
 
     if world > 1:
-        d = ShardedDPF(prf=prf, device=local_rank)
+        d = ShardedDPF(prf=prf, device=local_rank, reduce=args.reduce)
         d.eval_init(torch.from_numpy(table))
         inner = d._dpf
     else:
@@ -249,17 +264,31 @@ def run_ours(args):
     def step_device():
         d.eval_gpu_device(keys_dev, out_dev)
 
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()          # nvidia-smi needs a moment to produce its first sample
+    nwarm = max(args.warmup, 3)
+    t_warm = time.perf_counter()
+    for _ in range(nwarm):
         flush.zero_()
         step_device()
+    torch.cuda.synchronize()
+    # keep the GPU busy for ~0.5 s in total so the clock sampler sees it under load; the number
+    # of extra iterations is decided on rank 0 and broadcast (collectives must match across ranks)
+    per_step = (time.perf_counter() - t_warm) / nwarm
+    extra = torch.tensor([int(min(2000, max(0, 0.5 / max(per_step, 1e-6) - nwarm)))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(extra, src=0)
+    for i in range(int(extra.item())):
+        flush.zero_()
+        step_device()
+        if i % 16 == 15:
+            torch.cuda.synchronize()
+    nwarm += int(extra.item())
     torch.cuda.synchronize()
 
     import dpf_cpp
     launches_per_step = dpf_cpp.last_launches(inner.buffers)
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
@@ -333,19 +362,20 @@ def run_ours(args):
         published = BASELINE_PUBLISHED.get((args.prf, n)) if (entry == 16) else None
         line = {
             "metric": "DPFs/sec", "value": value, "unit": "DPFs/sec", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": nwarm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": (value / published) if published else None, "dtype": "u32",
             "data": "synthetic",
             "config": {"workload": "n=%d entry_size=%d %s batch=%d (512 per GPU), table entry-range sharded over %d GPU(s)"
                                    % (n, entry, args.prf.upper(), batch, world),
                        "n": n, "entry_size": entry, "prf": args.prf.upper(), "global_batch": batch,
-                       "parallelism": "entry-shard x%d + NCCL reduce" % world if world > 1 else "single GPU",
+                       "parallelism": ("entry-shard x%d + %s" % (world, "NCCL reduce" if args.reduce == "nccl" else
+                                       "in-kernel peer-memory red.add (symmetric memory)")) if world > 1 else "single GPU",
                        "l2": "256 MiB device buffer zeroed before every timed step (L2 flush); table 64 MiB",
                        "vs_baseline_ref": "reference README V100 number (BASELINE.md)" if published else None},
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
             "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     d.close()
     if world > 1:
         dist.destroy_process_group()
@@ -353,6 +383,12 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # Libraries (NCCL's version banner, torchrun notices) write to stdout; the contract is ONE
+    # JSON line there.  Point fd 1 at stderr for the whole run and print the line on the saved fd.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -199,7 +199,7 @@ int ensure_buffer(void **ptr, size_t *cap, size_t bytes)
  * (out = [nkeys][n] int32 share vectors).
  */
 int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, int mode_main, void *out_dev,
-                 cudaStream_t stream)
+                 cudaStream_t stream, bool clear_out = true)
 {
     const int nv = (mode_main != MODE_FUSED || c->entry_pad <= 16) ? 4 : (c->entry_pad <= 32 ? 8 : 16);
     const int passes = mode_main == MODE_FUSED ? c->entry_pad / (4 * nv) : 1;
@@ -245,7 +245,7 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
     rc = ensure_buffer(reinterpret_cast<void **>(&c->d_counters), &c->counters_cap, n_counters * sizeof(uint32_t));
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, n_counters * sizeof(uint32_t), stream));
-    if (mode_main == MODE_FUSED)
+    if (mode_main == MODE_FUSED && clear_out)
         CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)nkeys * c->entry_size * sizeof(int32_t), stream));
     c->last_launches = 0;
 
@@ -521,6 +521,15 @@ int b200dpf_eval_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
     return run_eval(c, keys_dev, nkeys, prf, out_dev, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int b200dpf_eval_device_acc(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *out_dev, void *cuda_stream)
+{
+    int rc = check_eval_args(c, keys_dev, nkeys, prf, out_dev);
+    if (rc) return rc;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    return run_pipeline(c, keys_dev, nkeys, prf, MODE_FUSED, out_dev, reinterpret_cast<cudaStream_t>(cuda_stream), false);
 }
 
 int b200dpf_expand_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *shares_dev, void *cuda_stream)

@@ -152,10 +152,11 @@ at::Tensor eval_gpu(const std::vector<at::Tensor> &keys, const std::vector<void 
 
 /* device-resident evaluation on the current torch stream handle passed as an integer */
 void eval_gpu_device(int64_t keys_ptr, int64_t nkeys, const std::vector<void *> &buffers, int prf, int64_t out_ptr,
-                     int64_t stream)
+                     int64_t stream, bool accumulate)
 {
-    check(b200dpf_eval_device(ctx_of(buffers), reinterpret_cast<const void *>(keys_ptr), nkeys, prf,
-                              reinterpret_cast<void *>(out_ptr), reinterpret_cast<void *>(stream)),
+    auto fn = accumulate ? b200dpf_eval_device_acc : b200dpf_eval_device;
+    check(fn(ctx_of(buffers), reinterpret_cast<const void *>(keys_ptr), nkeys, prf, reinterpret_cast<void *>(out_ptr),
+             reinterpret_cast<void *>(stream)),
           "eval_gpu_device");
 }
 
@@ -200,7 +201,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("eval_init_sharded", &eval_init_sharded, "eval_init for one entry-range shard", py::arg("table"),
           py::arg("device"), py::arg("shard_rank"), py::arg("shard_count"));
     m.def("eval_gpu_packed", &eval_gpu_packed, "eval_gpu with keys as one [B,524] tensor");
-    m.def("eval_gpu_device", &eval_gpu_device, "device-resident asynchronous evaluation");
+    m.def("eval_gpu_device", &eval_gpu_device, "device-resident asynchronous evaluation", py::arg("keys_ptr"),
+          py::arg("nkeys"), py::arg("buffers"), py::arg("prf"), py::arg("out_ptr"), py::arg("stream"),
+          py::arg("accumulate") = false);
     m.def("expand_gpu_device", &expand_gpu_device, "device-resident share-vector expansion");
     m.def("last_launches", &last_launches);
     m.def("set_subtree_log2", &set_subtree_log2);

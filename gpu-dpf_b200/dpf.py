@@ -128,18 +128,22 @@ class DPF(object):
             packed = torch.stack(list(keys))
         return dpf_cpp.eval_gpu_packed(packed, self.buffers, self.prf_method)
 
-    def eval_gpu_device(self, keys_dev, out_dev=None):
+    def eval_gpu_device(self, keys_dev, out_dev=None, out_ptr=None, accumulate=False):
         """Device-resident, asynchronous variant: keys_dev int32 [B,524] CUDA tensor ->
-        int32 [B, entry_size] CUDA tensor, enqueued on the current torch stream."""
+        int32 [B, entry_size] CUDA tensor, enqueued on the current torch stream.
+        accumulate=True adds into the destination instead of overwriting it; out_ptr may
+        then be a raw (e.g. peer-mapped) device address."""
         if self.buffers is None:
             raise Exception("Must call `eval_init` before `eval_gpu`")
         assert keys_dev.is_cuda and keys_dev.dtype == torch.int32 and keys_dev.is_contiguous()
-        if out_dev is None:
-            out_dev = torch.empty((keys_dev.shape[0], self.table_effective_entry_size), dtype=torch.int32,
-                                  device=keys_dev.device)
         stream = torch.cuda.current_stream(keys_dev.device).cuda_stream
+        if out_ptr is None:
+            if out_dev is None:
+                out_dev = torch.empty((keys_dev.shape[0], self.table_effective_entry_size), dtype=torch.int32,
+                                      device=keys_dev.device)
+            out_ptr = out_dev.data_ptr()
         dpf_cpp.eval_gpu_device(keys_dev.data_ptr(), keys_dev.shape[0], self.buffers, self.prf_method,
-                                out_dev.data_ptr(), stream)
+                                out_ptr, stream, accumulate)
         return out_dev
 
     def expand_gpu_device(self, keys_dev, out_dev=None):

@@ -1,12 +1,23 @@
-"""Entry-range sharding of one table across the GPUs of a box (one process per GPU).
+"""One table across the GPUs of a box: one process per GPU (torchrun), two axes.
 
-The reference is single-GPU.  A DPF evaluation is a sum
-over leaves, so disjoint leaf ranges give partial sums that add mod 2^32: rank r
-of G = 2^g owns the GGM subtree under the depth-g node with breadth-first index
-r (natural indices i with bitrev_g(i mod G) == r), holds only those n/G table
-rows, evaluates EVERY key over its subtree, and the [B, E] int32 partials meet in
-one NCCL reduce over NVLink (wrapping int32 add is exactly the required
-arithmetic).  No other data-path collective exists.
+The reference is single-GPU.
+
+axis="entries" (default) -- entry-range sharding.  A DPF evaluation is a sum over
+leaves, so disjoint leaf ranges give partial sums that add mod 2^32: rank r of
+G = 2^g owns the GGM subtree under the depth-g node with breadth-first index r
+(natural indices i with bitrev_g(i mod G) == r), holds only those n/G table rows,
+evaluates EVERY key over its subtree, and the [B, E] int32 partials are reduced
+to rank 0.  Two reductions are available:
+    reduce="nccl"   one dist.reduce(SUM, int32) over NVLink (wrapping int32 add is
+                    exactly the required arithmetic);
+    reduce="fused"  no collective kernel at all: every rank's evaluation kernel adds
+                    its partials straight into rank 0's result buffer through an
+                    NVLink peer mapping (torch symmetric memory), i.e. the kernel's
+                    red.global.add.u32 epilogue IS the reduction; two symmetric-
+                    memory barriers order the clearing and the consumption.
+axis="keys" -- replicas: every rank holds the whole table and evaluates a
+contiguous slice of the batch; results are gathered on rank 0.  No arithmetic
+crosses GPUs; right for small n where a shard would be tiny.
 
     dist.init_process_group("nccl")            # torchrun, one rank per GPU
     d = ShardedDPF(prf=DPF.PRF_AES128)         # device = LOCAL_RANK
@@ -37,37 +48,84 @@ def shard_indices(n, rank, world):
     return [brev(q, d - g) * world + c for q in range(n // world)]
 
 
-class ShardedDPF(object):
-    """dpf.DPF semantics over a process group; rank 0 receives the reduced result."""
+def key_slice(nkeys, rank, world):
+    """[begin, end) of the batch evaluated by `rank` on the keys axis."""
+    per = (nkeys + world - 1) // world
+    return min(rank * per, nkeys), min((rank + 1) * per, nkeys)
 
-    def __init__(self, prf=None, group=None, device=None, partial_fn=None):
-        # partial_fn(keys_packed_cpu_int32[B,524]) -> int32 [B,E] partial tensor on this rank's
-        # device.  Default: the CUDA engine.  Tests inject a CPU stand-in to exercise the
+
+class ShardedDPF(object):
+    """dpf.DPF semantics over a process group; rank 0 receives the result."""
+
+    def __init__(self, prf=None, group=None, device=None, axis="entries", reduce="nccl", partial_fn=None):
+        # partial_fn(keys_packed_cpu_int32[B,524]) -> int32 [B,E] tensor of this rank's
+        # contribution.  Default: the CUDA engine.  Tests inject a CPU stand-in to exercise the
         # process-group plumbing with the gloo backend.
+        assert axis in ("entries", "keys") and reduce in ("nccl", "fused")
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        if self.world & (self.world - 1):
+        if axis == "entries" and self.world & (self.world - 1):
             raise Exception("number of shards (%d) must be a power of two" % self.world)
         self.device = int(os.environ.get("LOCAL_RANK", self.rank)) if device is None else device
+        self.axis = axis
+        self.reduce = reduce if self.world > 1 else "nccl"
         self._partial_fn = partial_fn
         self._dpf = None
         self.prf = prf
         self.entry_size = None
         self.n = None
+        self._symm = None        # (tensor, handle, rank-0 base pointer) for reduce="fused"
 
     def eval_init(self, table):
         self.n, self.entry_size = table.shape[0], table.shape[1]
         if self._partial_fn is None:
             import dpf
-            self._dpf = dpf.DPF(prf=self.prf, device=self.device, shard=(self.rank, self.world))
+            shard = (self.rank, self.world) if self.axis == "entries" else (0, 1)
+            self._dpf = dpf.DPF(prf=self.prf, device=self.device, shard=shard)
             self._dpf.eval_init(table)
         return self
 
+    # -- fused reduction plumbing ------------------------------------------------
+    def _symm_buffer(self, nkeys):
+        import torch.distributed._symmetric_memory as symm_mem
+        need = nkeys * self.entry_size
+        if self._symm is None or self._symm[0].numel() < need:
+            dev = torch.device("cuda", self.device)
+            t = symm_mem.empty(max(need, 1 << 16), dtype=torch.int32, device=dev)
+            grp = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(t, grp.group_name)
+            self._symm = (t, hdl, int(hdl.buffer_ptrs[0]))
+        return self._symm
+
     # -- device-resident path (benchmarks, servers that keep keys on the GPU) --
     def eval_gpu_device(self, keys_dev, out_dev=None):
-        """Partial on this rank's stream followed by the reduce; returns the device tensor
-        (complete on rank 0 once the stream is synchronised)."""
+        """This rank's work on its stream, then the cross-GPU step.  Returns the device tensor
+        holding the complete [B, E] result on rank 0 once the stream is synchronised."""
+        nkeys = keys_dev.shape[0]
+        if self.axis == "keys":
+            b, e = key_slice(nkeys, self.rank, self.world)
+            dev = keys_dev.device
+            part = torch.zeros((max(e - b, 0), self.entry_size), dtype=torch.int32, device=dev)
+            if e > b:
+                self._dpf.eval_gpu_device(keys_dev[b:e], part)
+            per = (nkeys + self.world - 1) // self.world
+            padded = torch.zeros((per, self.entry_size), dtype=torch.int32, device=dev)
+            padded[:e - b] = part
+            gathered = [torch.empty_like(padded) for _ in range(self.world)] if self.rank == 0 else None
+            dist.gather(padded, gathered, dst=0, group=self.group)
+            if self.rank == 0:
+                return torch.cat(gathered)[:nkeys]
+            return None
+        if self.world > 1 and self.reduce == "fused":
+            t, hdl, root_ptr = self._symm_buffer(nkeys)
+            view = t[:nkeys * self.entry_size].view(nkeys, self.entry_size)
+            if self.rank == 0:
+                view.zero_()
+            hdl.barrier(channel=0)                 # destination cleared before anyone adds
+            self._dpf.eval_gpu_device(keys_dev, out_ptr=root_ptr, accumulate=True)
+            hdl.barrier(channel=1)                 # every rank's adds have landed
+            return view
         out_dev = self._dpf.eval_gpu_device(keys_dev, out_dev)
         if self.world > 1:
             dist.reduce(out_dev, dst=0, op=dist.ReduceOp.SUM, group=self.group)

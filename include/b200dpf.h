@@ -145,6 +145,18 @@ int b200dpf_eval_device(b200dpf_ctx *ctx, const void *keys_dev, int64_t nkeys, i
                         void *out_dev, void *cuda_stream);
 
 /*
+ * As b200dpf_eval_device, but ADDS the results into out_dev (mod 2^32) instead
+ * of overwriting it: out_dev is not cleared first.  With out_dev pointing at a
+ * peer GPU's buffer (NVLink peer mapping / symmetric memory) the kernel's
+ * red.global.add.u32 epilogue performs the cross-shard reduction itself, so
+ * sharded evaluation needs no separate collective (SURVEY.md section 8(e),
+ * "fused alternative").  The caller orders the clearing of the destination
+ * before, and its consumption after, all contributing launches.
+ */
+int b200dpf_eval_device_acc(b200dpf_ctx *ctx, const void *keys_dev, int64_t nkeys, int prf,
+                            void *out_dev, void *cuda_stream);
+
+/*
  * Non-fused full-domain expansion on the GPU (SURVEY.md section 8(f) rank 2;
  * the role of FUSES_MATMUL=0 in dpf_gpu/dpf/dpf_hybrid.cu:162-165, but in
  * natural index order): shares_dev[b][i] = low32(EvaluateFlat(key_b, i)) for

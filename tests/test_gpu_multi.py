@@ -36,9 +36,10 @@ def _worker(rank, world, port, ret):
     orc = O.Oracle()
     n = 1 << 14
     table = random_table(n, 16, seed=13)
-    for prf in (3, 2):
+    for prf, axis, reduce in ((3, "entries", "nccl"), (2, "entries", "nccl"), (3, "entries", "fused"),
+                              (1, "entries", "fused"), (3, "keys", "nccl")):
         ka, kb, idx = seeded_keys(b200dpf.gen, n, 70, prf, seed=17)
-        d = ShardedDPF(prf=prf)
+        d = ShardedDPF(prf=prf, axis=axis, reduce=reduce)
         d.eval_init(torch.from_numpy(table))
         got_a = d.eval_gpu(torch.from_numpy(ka))
         got_b = d.eval_gpu([torch.from_numpy(k) for k in kb])

@@ -7,10 +7,10 @@ run() { # label, env..., bench args
 {
 for s in 4 5 6 7 8; do run "aes n=2^20 frontier s=$s" B200DPF_S=$s python bench.py --no-cpu-baseline --no-e2e --steps 5; done
 run "aes n=2^20 nofrontier s=8" B200DPF_FRONTIER=0 python bench.py --no-cpu-baseline --no-e2e --steps 5
-for s in 3 4 5 6; do run "aes n=2^14 frontier s=$s" B200DPF_S=$s python bench.py --n 16384 --no-cpu-baseline --no-e2e --steps 20; done
-run "aes n=2^14 nofrontier" B200DPF_FRONTIER=0 python bench.py --n 16384 --no-cpu-baseline --no-e2e --steps 20
-for s in 4 5 6; do run "aes n=2^16 frontier s=$s" B200DPF_S=$s python bench.py --n 65536 --no-cpu-baseline --no-e2e --steps 20; done
-run "aes n=2^16 nofrontier" B200DPF_FRONTIER=0 python bench.py --n 65536 --no-cpu-baseline --no-e2e --steps 20
+for s in 3 4 5 6; do run "aes n=2^14 frontier s=$s" B200DPF_S=$s python bench.py --entries 16384 --no-cpu-baseline --no-e2e --steps 20; done
+run "aes n=2^14 nofrontier" B200DPF_FRONTIER=0 python bench.py --entries 16384 --no-cpu-baseline --no-e2e --steps 20
+for s in 4 5 6; do run "aes n=2^16 frontier s=$s" B200DPF_S=$s python bench.py --entries 65536 --no-cpu-baseline --no-e2e --steps 20; done
+run "aes n=2^16 nofrontier" B200DPF_FRONTIER=0 python bench.py --entries 65536 --no-cpu-baseline --no-e2e --steps 20
 for s in 5 6 7 8 10; do run "chacha n=2^20 frontier s=$s" B200DPF_S=$s python bench.py --prf chacha20 --no-cpu-baseline --no-e2e --steps 5; done
 run "chacha n=2^20 nofrontier" B200DPF_FRONTIER=0 python bench.py --prf chacha20 --no-cpu-baseline --no-e2e --steps 5
 run "aes n=2^20 E=128 B=512" python bench.py --entry 128 --no-cpu-baseline --no-e2e --steps 3
