@@ -125,6 +125,25 @@ at::Tensor eval_gpu_packed(const at::Tensor &keys, const std::vector<void *> &bu
     return result;
 }
 
+/* keys as a Python list of int32[524] CPU tensors, any length -> int32[len, E] CPU tensor
+ * (packing done here, not with torch.stack in Python) */
+at::Tensor eval_gpu_list(const std::vector<at::Tensor> &keys, const std::vector<void *> &buffers, int prf)
+{
+    b200dpf_ctx *ctx = ctx_of(buffers);
+    const int64_t total = (int64_t)keys.size();
+    const int64_t esz = b200dpf_ctx_entry_size(ctx);
+    at::Tensor result = torch::empty({total, esz}, at::kInt);
+    if (total == 0) return result;
+    std::vector<int32_t> packed((size_t)total * kKeyWords);
+    for (int64_t i = 0; i < total; i++)
+        std::memcpy(packed.data() + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_eval(ctx, packed.data(), total, prf, result.data_ptr<int32_t>()), "eval_gpu");
+    }
+    return result;
+}
+
 /* dpf_wrapper.cu:134-186.  The reference's dpf.py pads short batches by
  * repeating the LAST key object (dpf.py:126); trailing repeats of one tensor
  * are evaluated once and their rows replicated. */
@@ -201,6 +220,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("eval_init_sharded", &eval_init_sharded, "eval_init for one entry-range shard", py::arg("table"),
           py::arg("device"), py::arg("shard_rank"), py::arg("shard_count"));
     m.def("eval_gpu_packed", &eval_gpu_packed, "eval_gpu with keys as one [B,524] tensor");
+    m.def("eval_gpu_list", &eval_gpu_list, "eval_gpu with keys as a list of any length");
     m.def("eval_gpu_device", &eval_gpu_device, "device-resident asynchronous evaluation", py::arg("keys_ptr"),
           py::arg("nkeys"), py::arg("buffers"), py::arg("prf"), py::arg("out_ptr"), py::arg("stream"),
           py::arg("accumulate") = false);

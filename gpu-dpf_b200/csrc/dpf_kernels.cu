@@ -310,11 +310,19 @@ template <int PRF, int NV, int MODE>
 cudaError_t launch_one(const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
 {
     auto kern = dpf_eval_kernel<PRF, NV, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    /* function attributes are per device and sticky: set them once per (device, size) */
+    static int configured[64];   /* smem bytes + 1 last configured on each device, 0 = never */
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    /* the kernels live in shared memory; L1 only sees broadcast table rows */
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || configured[dev] != (int)smem + 1) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        /* the kernels live in shared memory; L1 only sees broadcast table rows */
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = (int)smem + 1;
+    }
     kern<<<grid, (KernelShape<PRF, NV>::THREADS), smem, stream>>>(p);
     return cudaGetLastError();
 }

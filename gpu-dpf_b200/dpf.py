@@ -121,12 +121,10 @@ class DPF(object):
         if self.buffers is None:
             raise Exception("Must call `eval_init` before `eval_gpu`")
         if isinstance(keys, torch.Tensor):
-            packed = keys.contiguous()
-        else:
-            if len(keys) == 0:
-                return torch.zeros((0, self.table_effective_entry_size), dtype=torch.int32)
-            packed = torch.stack(list(keys))
-        return dpf_cpp.eval_gpu_packed(packed, self.buffers, self.prf_method)
+            return dpf_cpp.eval_gpu_packed(keys.contiguous(), self.buffers, self.prf_method)
+        if len(keys) == 0:
+            return torch.zeros((0, self.table_effective_entry_size), dtype=torch.int32)
+        return dpf_cpp.eval_gpu_list(list(keys), self.buffers, self.prf_method)
 
     def eval_gpu_device(self, keys_dev, out_dev=None, out_ptr=None, accumulate=False):
         """Device-resident, asynchronous variant: keys_dev int32 [B,524] CUDA tensor ->
