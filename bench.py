@@ -57,7 +57,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"],
+                    help="reference = the reference's CPU path on the host cores; reference-gpu = the reference's "
+                         "own GPU kernel compiled unmodified for sm_100a (oracle/_ref/ref_dpf_cpp.so), 1 GPU")
     ap.add_argument("--entries", "--n", dest="n", type=int, default=1 << 20, help="table size n (use --entries under torchrun: --n is ambiguous to its parser)")
     ap.add_argument("--entry", type=int, default=16)
     ap.add_argument("--prf", default="aes128", choices=sorted(PRF_IDS))
@@ -212,6 +214,46 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def run_reference_gpu(args):
+    """The reference's dpf_hybrid_kernel on this box, measured the way its benchmark.py does
+    (dpf.py:286-320): wall clock around `steps` eval_gpu calls of 512 host key tensors."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import refgpu
+    if not refgpu.available():
+        emit({"impl": "reference-gpu", "unavailable": "oracle/_ref/ref_dpf_cpp.so not built (needs the reference tree)"})
+        return
+    prf = PRF_IDS[args.prf]
+    n, entry, batch = args.n, args.entry, args.batch_per_gpu
+    table = synthetic_table(n, entry)
+    keys_np, _ = synthetic_keys(n, batch, prf)
+    keys = [torch.from_numpy(k) for k in keys_np]
+    ref = refgpu.RefGpuDPF(prf)
+    t0 = time.perf_counter()
+    ref.eval_init(torch.from_numpy(table))
+    t_init = time.perf_counter() - t0
+    for _ in range(max(args.warmup, 1)):
+        ref.eval_gpu(keys)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = ref.eval_gpu(keys)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    value = batch * args.steps / dt
+    emit({"impl": "reference-gpu", "metric": "DPFs/sec", "value": value, "unit": "DPFs/sec", "n_gpus": 1,
+          "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * dt / args.steps,
+          "higher_is_better": True, "dtype": "u128", "data": "synthetic",
+          "config": {"workload": "n=%d entry_size=%d %s batch=%d, reference dpf_hybrid_kernel compiled for sm_100a, "
+                                 "wall clock incl. host marshalling (benchmark.py method)" % (n, entry, args.prf.upper(), batch),
+                     "eval_init_s": t_init},
+          "e2e": {"value": value, "unit": "DPFs/sec", "h2d_bytes_per_step": batch * 2080, "d2h_bytes_per_step": batch * 256},
+          "checksum": int(out.to(torch.int64).sum().item())})
+    ref.close()
 
 
 # ---------------------------------------------------------------------------
@@ -400,6 +442,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 
