@@ -153,13 +153,15 @@ int smem_layout(b200dpf_ctx *c, int prf, int nv, int mode, SmemLayout *L)
     return B200DPF_OK;
 }
 
-void fill_common(const b200dpf_ctx *c, const SmemLayout &L, int s, int64_t nkeys, EvalParams *p, size_t *smem)
+void fill_common(const b200dpf_ctx *c, const SmemLayout &L, int s, int64_t nkeys, int kpw_log2, EvalParams *p,
+                 size_t *smem)
 {
     std::memset(p, 0, sizeof *p);
     p->depth = c->depth;
     p->s = s;
     p->nkeys = (int)nkeys;
-    p->key_groups = (int)((nkeys + 31) / 32);
+    p->kpw_log2 = kpw_log2;
+    p->key_groups = (int)((nkeys + (1 << kpw_log2) - 1) >> kpw_log2);
     p->table = reinterpret_cast<const uint4 *>(c->d_table);
     p->row_stride_v = (uint32_t)c->entry_pad / 4u;
     p->out_stride = (uint32_t)c->entry_size;
@@ -206,8 +208,13 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
     SmemLayout L;
     int rc = smem_layout(c, prf, nv, mode_main, &L);
     if (rc) return rc;
-    const int64_t key_groups = (nkeys + 31) / 32;
     const int64_t warps = (int64_t)L.grid * (L.threads / 32);
+    /* keys per warp: a full warp of keys when the batch allows; for small batches the
+     * spare lanes take adjacent subtrees of the same keys (single-query latency mode) */
+    int kpw_log2 = 5;
+    if (env_int("B200DPF_LANE_SPLIT", 1) != 0)
+        while (kpw_log2 > 0 && ((int64_t)1 << (kpw_log2 - 1)) >= nkeys) kpw_log2--;
+    int64_t key_groups = (nkeys + ((int64_t)1 << kpw_log2) - 1) >> kpw_log2;
 
     /* ---- work-item size s and the frontier depth --------------------------------
      * measured on B200 (profiles/r1_sweeps.txt).  Without a frontier every item
@@ -228,17 +235,24 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         const int s_floor = want_frontier ? 3 : 5;
         const int64_t items_per_warp = want_frontier ? 24 : 6;
         s = std::min(c->depth_local, std::min(L.s_max, s_cap));
-        while (s > s_floor && (((int64_t)1 << (c->depth_local - s)) * key_groups) < items_per_warp * warps) s--;
+        while (s > s_floor &&
+               ((((int64_t)1 << (c->depth_local - s)) * key_groups) >> (5 - kpw_log2)) < items_per_warp * warps)
+            s--;
     }
     if (s < 1) s = 1;
     const int rel = c->depth_local - s;           /* tree levels between the shard root and the items */
+    if (5 - kpw_log2 > rel) {                     /* not enough subtrees to split a warp that far */
+        kpw_log2 = 5 - rel;
+        key_groups = (nkeys + ((int64_t)1 << kpw_log2) - 1) >> kpw_log2;
+    }
+    const int spw_log2 = 5 - kpw_log2;
 
     int f_rel = 0;                                /* frontier depth below the shard root (0 = none) */
     if (want_frontier && rel >= 2) {
         const int64_t cap_bytes = (int64_t)env_int("B200DPF_FRONTIER_MB", 256) << 20;
         f_rel = rel;
-        while (f_rel > 0 && ((key_groups * 512) << f_rel) > cap_bytes) f_rel--;
-        if (f_rel < 2) f_rel = 0;
+        while (f_rel > 0 && ((key_groups * (16 << kpw_log2)) << f_rel) > cap_bytes) f_rel--;
+        if (f_rel < 2 || f_rel < spw_log2 + 1) f_rel = 0;
     }
 
     const size_t n_counters = (size_t)(passes + 1) * (size_t)key_groups;
@@ -253,13 +267,13 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
     size_t smem;
     if (f_rel > 0) {
         rc = ensure_buffer(reinterpret_cast<void **>(&c->d_frontier), &c->frontier_cap,
-                           ((size_t)key_groups * 512) << f_rel);
+                           ((size_t)key_groups * (16 << kpw_log2)) << f_rel);
         if (rc) return rc;
         SmemLayout LF;
         rc = smem_layout(c, prf, 4, MODE_FRONTIER, &LF);
         if (rc) return rc;
-        const int s_top = std::min(f_rel, std::min(5, LF.s_max));
-        fill_common(c, LF, s_top, nkeys, &p, &smem);
+        const int s_top = std::max(1, std::min(f_rel - spw_log2, std::min(5, LF.s_max)));
+        fill_common(c, LF, s_top, nkeys, kpw_log2, &p, &smem);
         p.keys = reinterpret_cast<const uint4 *>(keys_dev);
         p.nsub = (uint32_t)1 << (f_rel - s_top);
         p.sub_first = (uint32_t)c->shard_rank << (f_rel - s_top);
@@ -273,7 +287,7 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         c->last_launches++;
     }
 
-    fill_common(c, L, s, nkeys, &p, &smem);
+    fill_common(c, L, s, nkeys, kpw_log2, &p, &smem);
     p.keys = reinterpret_cast<const uint4 *>(keys_dev);
     p.nsub = (uint32_t)1 << rel;
     p.sub_first = (uint32_t)c->shard_rank << rel;

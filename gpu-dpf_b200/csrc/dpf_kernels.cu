@@ -10,7 +10,11 @@
  *                 work item; LANE = KEY.  All 32 lanes walk the same tree shape,
  *                 so control flow is warp-uniform and every table row a warp
  *                 needs is ONE broadcast 128-bit load shared by 32 keys (the
- *                 reference re-reads the table once per key).
+ *                 reference re-reads the table once per key).  For batches
+ *                 smaller than a warp the mapping generalises to lane = (key,
+ *                 subtree slot): kpw keys x 32/kpw adjacent subtrees per warp, so a
+ *                 single query still uses every lane (the role the reference gives
+ *                 to dpf_coop.cu).
  *   expansion   = per-thread depth-first search: a node's two children are
  *                 produced together in registers (shared AES key schedule /
  *                 shared first-round quarter rounds), the right child parks in a
@@ -91,7 +95,8 @@ struct DevEnv {
     uint32_t row_stride_v;
     uint32_t acc[4 * NV];
     uint4 ra[4], rb[4];         /* prefetched first 64 bytes of the two rows of a leaf pair */
-    uint4 *front_out;           /* MODE_FRONTIER: &frontier[(kg*nfront + first node)*32 + lane] */
+    uint4 *front_out;           /* MODE_FRONTIER: &frontier[(kg*nfront + first node)*kpw + key slot] */
+    uint32_t kpw;               /* keys per warp */
     /* expand mode */
     uint32_t *share_row;        /* shares + key*n */
     uint32_t pos_base;          /* global leaf position of the subtree's first leaf */
@@ -166,8 +171,8 @@ struct DevEnv {
     /* MODE_FRONTIER: whole seeds of two adjacent frontier nodes */
     __device__ __forceinline__ void node_pair(uint32_t local_pos, const Seed &c0, const Seed &c1)
     {
-        front_out[(size_t)local_pos * 32] = make_uint4(c0.x, c0.y, c0.z, c0.w);
-        front_out[(size_t)(local_pos + 1) * 32] = make_uint4(c1.x, c1.y, c1.z, c1.w);
+        front_out[(size_t)local_pos * kpw] = make_uint4(c0.x, c0.y, c0.z, c0.w);
+        front_out[(size_t)(local_pos + 1) * kpw] = make_uint4(c1.x, c1.y, c1.z, c1.w);
     }
 };
 
@@ -192,9 +197,17 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
     uint4 *root_s = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_root);
     volatile int *flag_s = reinterpret_cast<volatile int *>(g_dyn_smem + p.off_flag);
 
+    /* lane -> (key slot within the group, subtree slot within the ticket) */
+    const int kpw = 1 << p.kpw_log2;
+    const int spw_log2 = 5 - p.kpw_log2;
+    const int kslot = lane & (kpw - 1);
+    const uint32_t sslot = (uint32_t)lane >> p.kpw_log2;
+    const uint32_t ntickets = p.nsub >> spw_log2;
+
     DevEnv<PRF, NV, THREADS, MODE> env;
-    env.cw_lane = cw_s + lane;
-    env.cwlo_lane = cwlo_s + lane;
+    env.cw_lane = cw_s + kslot;
+    env.cwlo_lane = cwlo_s + kslot;
+    env.kpw = (uint32_t)kpw;
     env.stack_lo = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_stack_lo) + tid;
     env.stack_hi = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_stack_hi) + tid - p.stack_split * THREADS;
     env.stack_split = p.stack_split;
@@ -219,26 +232,26 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
     for (int j = 0; j < p.key_groups; j++) {
         const int kg = (int)((blockIdx.x + (unsigned)j) % (unsigned)p.key_groups);
 
-        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(p.counters + kg) < p.nsub) ? 1 : 0;
+        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(p.counters + kg) < ntickets) ? 1 : 0;
         __syncthreads();
         const bool has_work = (*flag_s != 0);
         if (has_work) {
             /* correction words of this key group -> shared, [level][bank][bit][key] */
             const int per_key = p.depth * 4;
-            for (int i = tid; i < per_key * 32; i += THREADS) {
+            for (int i = tid; i < per_key * kpw; i += THREADS) {
                 const int k = i / per_key;            /* key within the group   */
                 const int e = i - k * per_key;        /* (bank, level, bit)     */
                 const int bank = e / (p.depth * 2);
                 const int lb = e - bank * (p.depth * 2);   /* 2*level + bit       */
-                int key = kg * 32 + k;
+                int key = kg * kpw + k;
                 if (key >= p.nkeys) key = p.nkeys - 1;
                 const uint4 v = __ldg(p.keys + (size_t)key * 131 + (bank ? 65 : 1) + lb);
                 const int level = lb >> 1, bit = lb & 1;
                 cw_s[((level * 2 + bank) * 2 + bit) * 32 + k] = v;
                 if (level == 0) cwlo_s[(bank * 2 + bit) * 32 + k] = v.x;
             }
-            if (tid < 32) {
-                int key = kg * 32 + tid;
+            if (tid < kpw) {
+                int key = kg * kpw + tid;
                 if (key >= p.nkeys) key = p.nkeys - 1;
                 root_s[tid] = __ldg(p.keys + (size_t)key * 131 + 129);
             }
@@ -246,7 +259,7 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
         __syncthreads();
         if (!has_work) continue;
 
-        const int key = kg * 32 + lane;
+        const int key = kg * kpw + kslot;
         env.key_valid = key < p.nkeys;
         if (MODE == MODE_FUSED) {
 #pragma unroll
@@ -254,22 +267,23 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
         } else if (MODE == MODE_EXPAND) {
             env.share_row = p.shares + (size_t)(env.key_valid ? key : 0) * p.n;
         }
-        const uint4 rv = root_s[lane];
+        const uint4 rv = root_s[kslot];
         const Seed root = make_seed(rv.x, rv.y, rv.z, rv.w);
 
         for (;;) {
-            uint32_t q = 0;
-            if (lane == 0) q = atomicAdd(p.counters + kg, 1u);
-            q = __shfl_sync(0xffffffffu, q, 0);
-            if (q >= p.nsub) break;
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(p.counters + kg, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= ntickets) break;
+            const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
             if (p.frontier_in != nullptr) {
-                const uint4 fv = p.frontier_in[((size_t)kg * p.nfront + (q >> p.front_shift)) * 32 + lane];
+                const uint4 fv = p.frontier_in[((size_t)kg * p.nfront + (q >> p.front_shift)) * kpw + kslot];
                 start = make_seed(fv.x, fv.y, fv.z, fv.w);
             }
             const Seed r = walk_down<PRF>(env, start, p.walk_first_level, p.walk_steps, p.sub_first + q);
             if (MODE == MODE_FRONTIER) {
-                env.front_out = p.frontier_out + ((size_t)kg * p.nfront + ((size_t)q << p.s)) * 32 + lane;
+                env.front_out = p.frontier_out + ((size_t)kg * p.nfront + ((size_t)q << p.s)) * kpw + kslot;
                 eval_subtree<PRF, true>(env, r, p.s, p.level_base);
             } else {
                 env.rows = p.table + ((size_t)q << p.s) * p.row_stride_v + p.col_off_v;
@@ -278,11 +292,19 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
             }
         }
 
-        if (MODE == MODE_FUSED && env.key_valid) {
-            uint32_t *o = p.out + (size_t)key * p.out_stride + p.col_off;
+        if (MODE == MODE_FUSED) {
+            /* lanes that hold the same key (different subtree slots) fold their partial sums
+             * first, so every key receives one red.add per warp and column, not 32/kpw */
+            for (int off = kpw; off < 32; off <<= 1) {
 #pragma unroll
-            for (int e = 0; e < 4 * NV; e++)
-                if ((uint32_t)e < p.ncols) atomicAdd(o + e, env.acc[e]);
+                for (int e = 0; e < 4 * NV; e++) env.acc[e] += __shfl_xor_sync(0xffffffffu, env.acc[e], off);
+            }
+            if (env.key_valid && sslot == 0) {
+                uint32_t *o = p.out + (size_t)key * p.out_stride + p.col_off;
+#pragma unroll
+                for (int e = 0; e < 4 * NV; e++)
+                    if ((uint32_t)e < p.ncols) atomicAdd(o + e, env.acc[e]);
+            }
         }
         __syncthreads();   /* everyone done with this group's correction words */
     }

@@ -13,7 +13,11 @@ namespace b200dpf {
 struct EvalParams {
     const uint4 *keys;        /* [nkeys][131] 128-bit slots, reference wire format      */
     int nkeys;
-    int key_groups;           /* ceil(nkeys / 32): one lane per key, 32 keys per warp   */
+    int kpw_log2;             /* log2 keys per warp (5 = one key per lane).  With fewer
+                                 keys than lanes the spare lanes take further subtrees of
+                                 the same keys: lane = (key = lane % kpw, subtree slot =
+                                 lane / kpw), so small batches still fill the warp       */
+    int key_groups;           /* ceil(nkeys / kpw)                                       */
     const uint4 *table;       /* this shard's rows in breadth-first leaf order          */
     uint32_t row_stride_v;    /* uint4 per table row (padded entry size / 4)            */
     uint32_t col_off_v;       /* first uint4 column of this pass                        */
@@ -25,7 +29,7 @@ struct EvalParams {
     int s;                    /* log2 leaves per work item (one warp = 32 keys x 2^s)   */
     /* where a work item starts: the key's root seed, or a node of a precomputed
      * frontier (seeds of every depth-F node of this shard, built by MODE 2)           */
-    const uint4 *frontier_in; /* [key_groups][nfront][32 keys] or null                  */
+    const uint4 *frontier_in; /* [key_groups][nfront][kpw keys] or null                 */
     uint4 *frontier_out;      /* MODE 2 output, same layout                             */
     uint32_t nfront;          /* frontier nodes per key (this shard)                    */
     int front_shift;          /* work item q starts at frontier node q >> front_shift   */
@@ -34,7 +38,8 @@ struct EvalParams {
     int level_base;           /* level of the subtree's bottom expansion (0 = leaves)   */
     uint32_t sub_first;       /* breadth-first index of the shard's first 2^s-subtree   */
     uint32_t nsub;            /* number of 2^s-subtrees in this shard                   */
-    uint32_t *counters;       /* [key_groups] work-item tickets, pre-zeroed             */
+    uint32_t *counters;       /* [key_groups] tickets, pre-zeroed; one ticket = 32/kpw
+                                 consecutive subtrees for the group's kpw keys          */
     /* expand mode (non-fused): shares[key][index], natural order                      */
     uint32_t *shares;
     uint64_t n;
