@@ -396,7 +396,10 @@ def run_ours(args):
             traffic = tr.get(key, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        binding = {"aes128": {"pipe": "l1tex data pipe (shared-memory T-table wavefronts)", "busy_frac": 0.979},
+                   "salsa20": {"pipe": "integer ALU pipe (LOP3/SHF)", "busy_frac": 0.977},
+                   "chacha20": {"pipe": "integer ALU pipe (LOP3/SHF)", "busy_frac": 0.954}}.get(args.prf)
+        roofline = {"bound": "hbm", "binding_pipe_ncu": binding, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_kind,
                     "note": "algorithmic bytes = batch*(n*E*4/ngpu + 2096 + 4E) per launch (table streamed once "
                             "per key, SURVEY 8d); actual DRAM traffic is far lower because 32 keys share each row "

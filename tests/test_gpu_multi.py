@@ -50,6 +50,18 @@ def _worker(rank, world, port, ret):
         else:
             assert got_a is None
         d.close()
+    # BASELINE config 5 shape (scaled down): entry_size 128, AES128, sharded, batch not a multiple of 32
+    n, entry, prf = 1 << 16, 128, 3
+    table = random_table(n, entry, seed=5)
+    ka, kb, idx = seeded_keys(b200dpf.gen, n, 45, prf, seed=6)
+    d = ShardedDPF(prf=prf)
+    d.eval_init(torch.from_numpy(table))
+    got_a, got_b = d.eval_gpu(torch.from_numpy(ka)), d.eval_gpu(torch.from_numpy(kb))
+    if rank == 0:
+        rec = (got_a.numpy().astype(np.uint32) - got_b.numpy().astype(np.uint32)).astype(np.int32)
+        assert np.array_equal(rec, table[idx])
+        assert np.array_equal(got_a.numpy()[:2], orc.eval_dot(ka[:2], prf, table))
+    d.close()
     if rank == 0:
         ret.put("ok")
     dist.barrier()
