@@ -87,6 +87,8 @@ struct b200dpf_ctx {
     size_t counters_cap = 0;  /* bytes */
     void *d_frontier = nullptr;
     size_t frontier_cap = 0;  /* bytes */
+    void *d_leaf_cache = nullptr;
+    size_t leaf_cache_cap = 0;  /* bytes */
     int sm_count = 0;
     uint32_t smem_base = 0;
     int s_override = 0;
@@ -309,6 +311,48 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         return B200DPF_OK;
     }
     p.out = reinterpret_cast<uint32_t *>(out_dev);
+    /* Wide entries (more than one 64-column pass): the first pass stores each leaf's low word
+     * (4 bytes x keys x leaves, coalesced), the remaining column blocks are MAC-only streaming
+     * passes over that cache instead of fresh tree expansions. */
+    const size_t cache_bytes = (size_t)key_groups * 32u * (size_t)c->n_local * sizeof(uint32_t);
+    const bool use_cache = passes > 1 && nv == 16 && kpw_log2 == 5 && env_int("B200DPF_LEAF_CACHE", 1) != 0 &&
+                           cache_bytes <= ((size_t)env_int("B200DPF_LEAF_CACHE_MB", 16384) << 20);
+    if (use_cache) {
+        rc = ensure_buffer(&c->d_leaf_cache, &c->leaf_cache_cap, cache_bytes);
+        if (rc) return rc;
+        p.leaf_cache = reinterpret_cast<uint32_t *>(c->d_leaf_cache);
+        p.n_local = (uint64_t)c->n_local;
+        p.col_off_v = 0;
+        p.col_off = 0;
+        p.ncols = (uint32_t)std::min(64, c->entry_size);
+        p.counters = c->d_counters;
+        CUDA_TRY(launch_eval(prf, nv, MODE_FUSED, p, L.grid, smem, stream));
+        c->last_launches++;
+        MacParams m;
+        std::memset(&m, 0, sizeof m);
+        m.leaf_cache = p.leaf_cache;
+        m.table = p.table;
+        m.row_stride_v = p.row_stride_v;
+        m.out = p.out;
+        m.out_stride = p.out_stride;
+        m.nkeys = (int)nkeys;
+        m.key_groups = (int)key_groups;
+        m.n_local = (uint64_t)c->n_local;
+        const int mac_grid = c->sm_count * 2;                      /* 2 blocks x 8 warps per SM */
+        const int64_t mac_warps = (int64_t)mac_grid * 8;
+        int64_t ranges = std::max<int64_t>(1, (2 * mac_warps + key_groups - 1) / key_groups);
+        ranges = std::min<int64_t>(ranges, std::max<int64_t>(1, c->n_local / 64));
+        m.ranges_per_group = (uint32_t)ranges;
+        for (int pass = 1; pass < passes; pass++) {
+            m.col_off_v = (uint32_t)(pass * nv);
+            m.col_off = (uint32_t)(pass * 4 * nv);
+            m.ncols = (uint32_t)std::max(0, std::min(4 * nv, c->entry_size - pass * 4 * nv));
+            if (m.ncols == 0) break;
+            CUDA_TRY(launch_mac(nv, m, mac_grid, stream));
+            c->last_launches++;
+        }
+        return B200DPF_OK;
+    }
     for (int pass = 0; pass < passes; pass++) {
         p.col_off_v = (uint32_t)(pass * nv);
         p.col_off = (uint32_t)(pass * 4 * nv);
@@ -489,6 +533,7 @@ int b200dpf_destroy(b200dpf_ctx *c)
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_frontier) cudaFree(c->d_frontier);
+    if (c->d_leaf_cache) cudaFree(c->d_leaf_cache);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B200DPF_OK;

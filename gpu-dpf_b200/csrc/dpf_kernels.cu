@@ -95,6 +95,7 @@ struct DevEnv {
     uint32_t row_stride_v;
     uint32_t acc[4 * NV];
     uint4 ra[4], rb[4];         /* prefetched first 64 bytes of the two rows of a leaf pair */
+    uint32_t *leaf_out;         /* leaf cache slot of the subtree's first leaf for this lane, or null */
     uint4 *front_out;           /* MODE_FRONTIER: &frontier[(kg*nfront + first node)*kpw + key slot] */
     uint32_t kpw;               /* keys per warp */
     /* expand mode */
@@ -139,6 +140,10 @@ struct DevEnv {
     __device__ __forceinline__ void leaf_pair(uint32_t local_pos, uint32_t v0, uint32_t v1)
     {
         if (MODE == MODE_FUSED) {
+            if (NV == 16 && leaf_out != nullptr) {   /* coalesced: 32 keys x 4 bytes per leaf */
+                leaf_out[(size_t)local_pos * 32] = v0;
+                leaf_out[(size_t)(local_pos + 1) * 32] = v1;
+            }
             const uint4 *r = rows + (size_t)local_pos * row_stride_v;
 #pragma unroll
             for (int c = 0; c < NV / 4; c++) {
@@ -288,6 +293,8 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
             } else {
                 env.rows = p.table + ((size_t)q << p.s) * p.row_stride_v + p.col_off_v;
                 env.pos_base = (p.sub_first + q) << p.s;
+                env.leaf_out = p.leaf_cache ? p.leaf_cache + ((size_t)kg * p.n_local + ((size_t)q << p.s)) * 32 + lane
+                                            : nullptr;
                 eval_subtree<PRF, false>(env, r, p.s, 0);
             }
         }
@@ -307,6 +314,73 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
             }
         }
         __syncthreads();   /* everyone done with this group's correction words */
+    }
+}
+
+/* MAC-only pass for wide entries: leaves come from the cache written by the first fused
+ * pass, rows are broadcast loads as in the fused kernel.  One warp = 32 keys x one range
+ * of leaf positions; pure streaming (HBM/L2 -> IMAD), no PRF work. */
+template <int NV>
+__global__ void __launch_bounds__(256, 2) dpf_mac_kernel(const __grid_constant__ MacParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t warps_total = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t items = (uint64_t)p.key_groups * p.ranges_per_group;
+    const uint64_t len = (p.n_local + p.ranges_per_group - 1) / p.ranges_per_group;
+    for (uint64_t w = warp_global; w < items; w += warps_total) {
+        /* key group is the fast index: warps running at the same time stream the same table
+         * rows for different key groups, so the rows are read from DRAM once and hit in L2 after */
+        const uint32_t r = (uint32_t)(w / (uint64_t)p.key_groups);
+        const uint32_t kg = (uint32_t)(w - (uint64_t)r * p.key_groups);
+        const uint64_t begin = (uint64_t)r * len;
+        const uint64_t end = begin + len < p.n_local ? begin + len : p.n_local;
+        uint32_t acc[4 * NV];
+#pragma unroll
+        for (int e = 0; e < 4 * NV; e++) acc[e] = 0;
+        const uint32_t *leaf = p.leaf_cache + ((size_t)kg * p.n_local + begin) * 32 + lane;
+        const uint4 *row = p.table + begin * p.row_stride_v + p.col_off_v;
+        uint64_t pos = begin;
+        for (; pos + 4 <= end; pos += 4) {   /* 4 leaves per trip: 4 independent load streams in flight */
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = __ldg(leaf + 32 * u);
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                uint4 t[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) t[u] = __ldg(row + (size_t)u * p.row_stride_v + j);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    acc[4 * j + 0] += v[u] * t[u].x;
+                    acc[4 * j + 1] += v[u] * t[u].y;
+                    acc[4 * j + 2] += v[u] * t[u].z;
+                    acc[4 * j + 3] += v[u] * t[u].w;
+                }
+            }
+            leaf += 128;
+            row += (size_t)4 * p.row_stride_v;
+        }
+        for (; pos < end; pos++) {
+            const uint32_t v = __ldg(leaf);
+#pragma unroll
+            for (int j = 0; j < NV; j++) {
+                const uint4 t = __ldg(row + j);
+                acc[4 * j + 0] += v * t.x;
+                acc[4 * j + 1] += v * t.y;
+                acc[4 * j + 2] += v * t.z;
+                acc[4 * j + 3] += v * t.w;
+            }
+            leaf += 32;
+            row += p.row_stride_v;
+        }
+        const int key = (int)kg * 32 + lane;
+        if (key < p.nkeys) {
+            uint32_t *o = p.out + (size_t)key * p.out_stride + p.col_off;
+#pragma unroll
+            for (int e = 0; e < 4 * NV; e++)
+                if ((uint32_t)e < p.ncols) atomicAdd(o + e, acc[e]);
+        }
     }
 }
 
@@ -437,6 +511,15 @@ cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes)
     case PRF_AES128: return max_smem_prf<PRF_AES128>(nv, mode, bytes);
     default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_mac(int nv, const MacParams &p, int grid, cudaStream_t stream)
+{
+    if (nv == 4) dpf_mac_kernel<4><<<grid, 256, 0, stream>>>(p);
+    else if (nv == 8) dpf_mac_kernel<8><<<grid, 256, 0, stream>>>(p);
+    else if (nv == 16) dpf_mac_kernel<16><<<grid, 256, 0, stream>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_permute_table(const int32_t *stage, int32_t *table, uint64_t rows, int bits,

@@ -40,6 +40,10 @@ struct EvalParams {
     uint32_t nsub;            /* number of 2^s-subtrees in this shard                   */
     uint32_t *counters;       /* [key_groups] tickets, pre-zeroed; one ticket = 32/kpw
                                  consecutive subtrees for the group's kpw keys          */
+    /* wide entries: the first pass also stores every leaf's low word, [key group][leaf
+     * position][32 keys], so further column blocks are MAC-only (launch_mac)          */
+    uint32_t *leaf_cache;
+    uint64_t n_local;         /* leaves in this shard                                   */
     /* expand mode (non-fused): shares[key][index], natural order                      */
     uint32_t *shares;
     uint64_t n;
@@ -75,6 +79,20 @@ cudaError_t upload_aes_table(const uint32_t *te0_256);
  * grid = number of persistent blocks; smem_bytes = dynamic shared memory. */
 cudaError_t launch_eval(int prf, int nv, int mode, const EvalParams &p, int grid, size_t smem_bytes,
                         cudaStream_t stream);
+
+/* MAC-only pass over cached leaves: out[key][col_off + c] += sum_pos leaf[kg][pos][key] *
+ * table[pos][col_off + c] for the nv*4 columns starting at col_off_v (nv = 4, 8 or 16). */
+struct MacParams {
+    const uint32_t *leaf_cache;   /* [key_groups][n_local][32] */
+    const uint4 *table;
+    uint32_t row_stride_v, col_off_v;
+    uint32_t *out;
+    uint32_t out_stride, col_off, ncols;
+    int nkeys, key_groups;
+    uint64_t n_local;
+    uint32_t ranges_per_group;    /* position ranges a key group is cut into (one warp each) */
+};
+cudaError_t launch_mac(int nv, const MacParams &p, int grid, cudaStream_t stream);
 
 /* Maximum dynamic shared memory the evaluation kernel may be given. */
 cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes);
