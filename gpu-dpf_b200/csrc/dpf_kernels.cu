@@ -329,10 +329,9 @@ __global__ void __launch_bounds__(256, 2) dpf_mac_kernel(const __grid_constant__
     const uint64_t items = (uint64_t)p.key_groups * p.ranges_per_group;
     const uint64_t len = (p.n_local + p.ranges_per_group - 1) / p.ranges_per_group;
     for (uint64_t w = warp_global; w < items; w += warps_total) {
-        /* key group is the fast index: warps running at the same time stream the same table
-         * rows for different key groups, so the rows are read from DRAM once and hit in L2 after */
-        const uint32_t r = (uint32_t)(w / (uint64_t)p.key_groups);
-        const uint32_t kg = (uint32_t)(w - (uint64_t)r * p.key_groups);
+        /* range is the fast index (key-group-fast ordering measured slower: 30.4 vs 29.2 ms at E=128) */
+        const uint32_t kg = (uint32_t)(w / p.ranges_per_group);
+        const uint32_t r = (uint32_t)(w - (uint64_t)kg * p.ranges_per_group);
         const uint64_t begin = (uint64_t)r * len;
         const uint64_t end = begin + len < p.n_local ? begin + len : p.n_local;
         uint32_t acc[4 * NV];

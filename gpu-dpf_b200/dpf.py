@@ -144,6 +144,47 @@ class DPF(object):
                                 out_ptr, stream, accumulate)
         return out_dev
 
+    def eval_gpu_pipelined(self, batches, depth=2):
+        """Server loop over a stream of batches: yields one CPU
+        int32 [B, entry_size] tensor per input batch, in order.  Each batch is an int32 [B, 524]
+        CPU tensor (pinned memory makes the copies truly asynchronous).  The host-to-device copy of
+        batch i+1 and the device-to-host copy of batch i-1 run on their own streams while batch i
+        is being evaluated, so in steady state only the kernel time is exposed."""
+        if self.buffers is None:
+            raise Exception("Must call `eval_init` before `eval_gpu`")
+        dev = torch.device("cuda", self.device)
+        compute = torch.cuda.current_stream(dev)
+        h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        inflight = []                      # (out_host, done_event)
+
+        def drain(limit):
+            while len(inflight) > limit:
+                out_host, done = inflight.pop(0)
+                done.synchronize()
+                yield out_host
+
+        for keys in batches:
+            keys = keys.contiguous()
+            with torch.cuda.stream(h2d):
+                keys_dev = keys.to(dev, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(h2d)
+            compute.wait_event(copied)
+            keys_dev.record_stream(compute)
+            out_dev = self.eval_gpu_device(keys_dev)
+            computed = torch.cuda.Event()
+            computed.record(compute)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(computed)
+                out_dev.record_stream(d2h)
+                out_host = torch.empty(out_dev.shape, dtype=torch.int32, pin_memory=True)
+                out_host.copy_(out_dev, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(d2h)
+            inflight.append((out_host, done))
+            yield from drain(depth)
+        yield from drain(0)
+
     def expand_gpu_device(self, keys_dev, out_dev=None):
         """Share vectors on the GPU (the eval_cpu(one_hot_only=True) quantity): int32 [B, n] CUDA tensor."""
         if self.buffers is None:
