@@ -18,7 +18,7 @@ PRF_NAMES = {0: "DUMMY", 1: "SALSA20", 2: "CHACHA20", 3: "AES128"}
 
 # every symbol include/b200dpf.h declares
 SYMBOLS = [
-    "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_batch", "b200dpf_eval_cpu",
+    "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_eval_cpu",
     "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
     "b200dpf_eval_device", "b200dpf_eval_device_acc", "b200dpf_expand_device", "b200dpf_ctx_n", "b200dpf_ctx_entry_size",
     "b200dpf_ctx_device", "b200dpf_ctx_last_launches", "b200dpf_ctx_set_subtree_log2",
@@ -40,6 +40,7 @@ def load():
     L.b200dpf_version.restype = C.c_char_p
     L.b200dpf_last_error.restype = C.c_char_p
     L.b200dpf_gen.argtypes = [C.c_int64, C.c_int64, C.c_char_p, C.c_size_t, C.c_int, _i32p, _i32p]
+    L.b200dpf_gen_secure.argtypes = [C.c_int64, C.c_int64, C.c_char_p, C.c_size_t, C.c_int, _i32p, _i32p]
     L.b200dpf_gen_batch.argtypes = [_i64p, _u32p, C.c_int64, C.c_int64, C.c_int, C.c_int, _i32p, _i32p]
     L.b200dpf_eval_cpu.argtypes = [_i32p, C.c_int, _i32p]
     L.b200dpf_key_n.argtypes = [_i32p]
@@ -80,6 +81,13 @@ def gen(alpha, n, seed32, prf):
     b = np.zeros(KEY_WORDS, np.int32)
     seed = int(seed32 & 0xFFFFFFFF).to_bytes(4, "little")
     _check(lib().b200dpf_gen(alpha, n, seed, len(seed), prf, a, b), "b200dpf_gen")
+    return a, b
+
+
+def gen_secure(alpha, n, seed_bytes, prf):
+    a = np.zeros(KEY_WORDS, np.int32)
+    b = np.zeros(KEY_WORDS, np.int32)
+    _check(lib().b200dpf_gen_secure(alpha, n, bytes(seed_bytes), len(seed_bytes), prf, a, b), "b200dpf_gen_secure")
     return a, b
 
 

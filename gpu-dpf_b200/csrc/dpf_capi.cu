@@ -400,6 +400,17 @@ int b200dpf_gen(int64_t alpha, int64_t n, const uint8_t *seed, size_t seed_len, 
     return B200DPF_OK;
 }
 
+int b200dpf_gen_secure(int64_t alpha, int64_t n, const uint8_t *seed, size_t seed_len, int prf,
+                       int32_t *key_a, int32_t *key_b)
+{
+    if (!key_a || !key_b) return fail(B200DPF_EINVAL, "null key buffer");
+    if (!seed || seed_len < 44) return fail(B200DPF_EINVAL, "gen_secure needs at least 44 bytes of seed (got %zu)", seed_len);
+    if (host::gen_secure(alpha, n, seed, prf, key_a, key_b) != 0)
+        return fail(B200DPF_EINVAL, "gen_secure: need power-of-two n >= 2, 0 <= alpha < n, valid prf (alpha=%lld n=%lld prf=%d)",
+                    (long long)alpha, (long long)n, prf);
+    return B200DPF_OK;
+}
+
 int b200dpf_gen_batch(const int64_t *alphas, const uint32_t *seeds32, int64_t count, int64_t n, int prf,
                       int nthreads, int32_t *keys_a, int32_t *keys_b)
 {

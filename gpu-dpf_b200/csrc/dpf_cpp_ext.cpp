@@ -58,6 +58,17 @@ std::vector<at::Tensor> gen(int64_t k, int64_t n, const std::string &seed, int p
     return {a, b};
 }
 
+/* same construction from a ChaCha20 DRBG keyed by >= 44 bytes of caller entropy */
+std::vector<at::Tensor> gen_secure(int64_t k, int64_t n, const std::string &seed, int prf)
+{
+    at::Tensor a = torch::zeros({kKeyWords}, at::kInt);
+    at::Tensor b = torch::zeros({kKeyWords}, at::kInt);
+    check(b200dpf_gen_secure(k, n, reinterpret_cast<const uint8_t *>(seed.data()), seed.size(), prf,
+                             a.data_ptr<int32_t>(), b.data_ptr<int32_t>()),
+          "gen_secure");
+    return {a, b};
+}
+
 /* batched keygen: alphas int64[B], seeds int64[B] (low 32 bits used) -> two int32[B,524] tensors */
 std::vector<at::Tensor> gen_batch(const at::Tensor &alphas, int64_t n, const at::Tensor &seeds, int prf, int nthreads)
 {
@@ -215,6 +226,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     /* additions */
     m.attr("NATIVE_SHAPES") = py::int_(1);
     m.def("version", []() { return std::string(b200dpf_version()); });
+    m.def("gen_secure", &gen_secure, "dpf gen from a ChaCha20 DRBG (seed: >= 44 bytes)");
     m.def("gen_batch", &gen_batch, "batched multi-threaded keygen", py::arg("alphas"), py::arg("n"), py::arg("seeds"),
           py::arg("prf"), py::arg("nthreads") = 0);
     m.def("eval_init_sharded", &eval_init_sharded, "eval_init for one entry-range shard", py::arg("table"),

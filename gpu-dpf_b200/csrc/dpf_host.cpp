@@ -68,27 +68,82 @@ void set_slot(int32_t *key, int slot, u128 v)
 
 u128 prf128(int prf_id, u128 seed, uint32_t pos) { return to_u128(prf(prf_id, from_u128(seed), pos)); }
 
-/* dpf_base/dpf.h:272-283 */
-u128 random128(std::mt19937 &g)
-{
-    std::uniform_int_distribution<uint64_t> d(0, std::numeric_limits<uint64_t>::max());
-    const uint64_t hi = d(g);
-    const uint64_t lo = d(g);
-    return ((u128)hi << 64) | lo;
-}
+/* The reference's generator: std::mt19937 behind the draws of dpf_base/dpf.h:272-283
+ * (128-bit = two 64-bit uniform draws, high half first) and :450 (32-bit upper-level words). */
+struct ReferenceRng {
+    std::mt19937 g;
+    explicit ReferenceRng(uint32_t seed32) : g(seed32) {}
+    u128 draw128()
+    {
+        std::uniform_int_distribution<uint64_t> d(0, std::numeric_limits<uint64_t>::max());
+        const uint64_t hi = d(g);
+        const uint64_t lo = d(g);
+        return ((u128)hi << 64) | lo;
+    }
+    u128 draw_upper_cw() { return (u128)g(); }
+};
 
-u128 random128_odd(std::mt19937 &g)
+/* ChaCha20 (RFC 8439 block function) keystream as a deterministic random bit generator. */
+struct ChaCha20Rng {
+    uint32_t state[16];
+    uint32_t block[16];
+    int used = 16;
+    ChaCha20Rng(const uint8_t key[32], const uint8_t nonce[12])
+    {
+        static const uint32_t sigma[4] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+        for (int i = 0; i < 4; i++) state[i] = sigma[i];
+        for (int i = 0; i < 8; i++) std::memcpy(&state[4 + i], key + 4 * i, 4);
+        state[12] = 0;
+        for (int i = 0; i < 3; i++) std::memcpy(&state[13 + i], nonce + 4 * i, 4);
+    }
+    static uint32_t rl(uint32_t v, int r) { return (v << r) | (v >> (32 - r)); }
+    static void qr(uint32_t *x, int a, int b, int c, int d)
+    {
+        x[a] += x[b]; x[d] = rl(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rl(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rl(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rl(x[b] ^ x[c], 7);
+    }
+    void refill()
+    {
+        uint32_t x[16];
+        std::memcpy(x, state, sizeof x);
+        for (int r = 0; r < 10; r++) {
+            qr(x, 0, 4, 8, 12); qr(x, 1, 5, 9, 13); qr(x, 2, 6, 10, 14); qr(x, 3, 7, 11, 15);
+            qr(x, 0, 5, 10, 15); qr(x, 1, 6, 11, 12); qr(x, 2, 7, 8, 13); qr(x, 3, 4, 9, 14);
+        }
+        for (int i = 0; i < 16; i++) block[i] = x[i] + state[i];
+        state[12]++;
+        used = 0;
+    }
+    uint32_t draw32()
+    {
+        if (used == 16) refill();
+        return block[used++];
+    }
+    u128 draw128()
+    {
+        u128 v = 0;
+        for (int i = 0; i < 4; i++) v |= (u128)draw32() << (32 * i);
+        return v;
+    }
+    u128 draw_upper_cw() { return draw128(); }
+};
+
+template <class Rng>
+u128 random128_odd(Rng &g)
 {
     u128 k = 0;
-    while ((k & 1) == 0) k = random128(g);
+    while ((k & 1) == 0) k = g.draw128();
     return k;
 }
 
+template <class Rng>
 struct KeyBuilder {
     int depth;
     int64_t alpha;
     int prf_id;
-    std::mt19937 &g;
+    Rng &g;
     u128 cw1[64], cw2[64];
     u128 root_a, root_b;
 
@@ -100,7 +155,7 @@ struct KeyBuilder {
         u128 up_a, up_b;   /* seeds entering this level on the alpha path */
         if (L == depth - 1) {
             /* N = 2 base: one seed per server, differing in the LSB (dpf.h:318-331) */
-            u128 ka = random128(g), kb = random128(g);
+            u128 ka = g.draw128(), kb = g.draw128();
             ka &= ~(u128)1;
             kb = (kb & ~(u128)1) | 1;
             root_a = ka;
@@ -111,7 +166,7 @@ struct KeyBuilder {
                 if (i == row) delta[i] -= beta;
             }
             for (int i = 0; i < 2; i++) {
-                cw1[2 * L + i] = random128(g);
+                cw1[2 * L + i] = g.draw128();
                 cw2[2 * L + i] = cw1[2 * L + i] + delta[i];
             }
             up_a = ka;
@@ -125,7 +180,7 @@ struct KeyBuilder {
             for (int i = 0; i < 2; i++) {
                 u128 d = prf128(prf_id, up_b, (uint32_t)i) - prf128(prf_id, up_a, (uint32_t)i);
                 if (a_even) d = (u128)0 - d;
-                cw1[2 * L + i] = (u128)g();   /* 32-bit draw, dpf.h:450 */
+                cw1[2 * L + i] = g.draw_upper_cw();   /* reference: a 32-bit draw, dpf.h:450 */
                 cw2[2 * L + i] = cw1[2 * L + i] + d;
                 if (i == row) cw1[2 * L + i] += a_even ? beta : (u128)0 - beta;
             }
@@ -180,7 +235,10 @@ int64_t key_n(const int32_t *key)
     return n;
 }
 
-int gen(int64_t alpha, int64_t n, uint32_t seed32, int prf_id, int32_t *key_a, int32_t *key_b)
+namespace {
+
+template <class Rng>
+int gen_with(Rng &rng, int64_t alpha, int64_t n, int prf_id, int32_t *key_a, int32_t *key_b)
 {
     if (n < 2 || (n & (n - 1)) != 0 || alpha < 0 || alpha >= n) return -1;
     if (prf_id < PRF_DUMMY || prf_id > PRF_AES128) return -1;
@@ -188,8 +246,7 @@ int gen(int64_t alpha, int64_t n, uint32_t seed32, int prf_id, int32_t *key_a, i
     while (((int64_t)1 << depth) < n) depth++;
     if (depth > 32) return -1;
 
-    std::mt19937 g(seed32);   /* dpf_wrapper.cu:52: only 32 bits of the seed reach the engine */
-    KeyBuilder kb{depth, alpha, prf_id, g, {}, {}, 0, 0};
+    KeyBuilder<Rng> kb{depth, alpha, prf_id, rng, {}, {}, 0, 0};
     std::memset(kb.cw1, 0, sizeof kb.cw1);
     std::memset(kb.cw2, 0, sizeof kb.cw2);
     kb.build(0, (u128)1);   /* beta = 1, dpf_wrapper.cu:53 */
@@ -206,6 +263,20 @@ int gen(int64_t alpha, int64_t n, uint32_t seed32, int prf_id, int32_t *key_a, i
         set_slot(key, SLOT_N, (u128)n);
     }
     return 0;
+}
+
+}  // namespace
+
+int gen(int64_t alpha, int64_t n, uint32_t seed32, int prf_id, int32_t *key_a, int32_t *key_b)
+{
+    ReferenceRng rng(seed32);   /* dpf_wrapper.cu:52: only 32 bits of the seed reach the engine */
+    return gen_with(rng, alpha, n, prf_id, key_a, key_b);
+}
+
+int gen_secure(int64_t alpha, int64_t n, const uint8_t seed[44], int prf_id, int32_t *key_a, int32_t *key_b)
+{
+    ChaCha20Rng rng(seed, seed + 32);
+    return gen_with(rng, alpha, n, prf_id, key_a, key_b);
 }
 
 namespace {

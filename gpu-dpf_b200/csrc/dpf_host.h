@@ -35,6 +35,8 @@ int key_depth(const int32_t *key);
 int64_t key_n(const int32_t *key);
 
 int gen(int64_t alpha, int64_t n, uint32_t seed32, int prf_id, int32_t *key_a, int32_t *key_b);
+/* ChaCha20-DRBG variant: key = seed[0..31], nonce = seed[32..43] */
+int gen_secure(int64_t alpha, int64_t n, const uint8_t seed[44], int prf_id, int32_t *key_a, int32_t *key_b);
 int eval_cpu(const int32_t *key, int prf_id, int32_t *out_n);
 
 }  // namespace host

@@ -67,8 +67,10 @@ class DPF(object):
         self.prf_method_string = self._PRF_NAMES[self.prf_method]
 
     # ---- client -----------------------------------------------------------
-    def gen(self, k, n, seed=None):
-        """Two keys for the point function at index k over a domain of n (dpf.py:63-74)."""
+    def gen(self, k, n, seed=None, secure=False):
+        """Two keys for the point function at index k over a domain of n (dpf.py:63-74).
+        secure=True draws every random word from a ChaCha20 DRBG keyed by the seed (the
+        reference's generator only consumes 32 bits of it, dpf_wrapper.cu:52)."""
         if seed is None:
             seed = os.urandom(128)
         if n & (n - 1) != 0:
@@ -76,6 +78,8 @@ class DPF(object):
         if k >= n:
             raise Exception("k (%d), the selected element, must be less than n (%d), the number of entries in the table"
                             % (k, n))
+        if secure:
+            return dpf_cpp.gen_secure(k, n, seed, self.prf_method)
         return dpf_cpp.gen(k, n, seed, self.prf_method)
 
     def gen_batch(self, indices, n, seeds=None, nthreads=0):

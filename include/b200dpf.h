@@ -78,6 +78,18 @@ int b200dpf_gen(int64_t alpha, int64_t n, const uint8_t *seed, size_t seed_len,
                 int prf, int32_t *key_a, int32_t *key_b);
 
 /*
+ * Key generation from a cryptographic generator (the
+ * reference's own TODO at dpf.py:65 "replace with secure 128-bit RNG").  Same DPF
+ * construction and wire format, but every random draw -- including the upper-level
+ * correction words, which the reference draws as 32-bit values (dpf_base/dpf.h:450) --
+ * is 128 bits of a ChaCha20 (RFC 8439) keystream keyed with seed[0..31] and nonce
+ * seed[32..43].  seed_len must be >= 44 bytes of caller entropy.  Keys differ from
+ * b200dpf_gen's for the same seed; they evaluate with the same entry points.
+ */
+int b200dpf_gen_secure(int64_t alpha, int64_t n, const uint8_t *seed, size_t seed_len,
+                       int prf, int32_t *key_a, int32_t *key_b);
+
+/*
  * Batched key generation: `count` independent
  * b200dpf_gen calls spread over `nthreads` host threads (0 = all cores).
  * alphas[count]; seeds32[count] (one 32-bit generator seed per key);
