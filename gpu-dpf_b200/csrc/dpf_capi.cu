@@ -205,8 +205,16 @@ int ensure_buffer(void **ptr, size_t *cap, size_t bytes)
 int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, int mode_main, void *out_dev,
                  cudaStream_t stream, bool clear_out = true)
 {
-    const int nv = (mode_main != MODE_FUSED || c->entry_pad <= 16) ? 4 : (c->entry_pad <= 32 ? 8 : 16);
-    const int passes = mode_main == MODE_FUSED ? c->entry_pad / (4 * nv) : 1;
+    /* Entries wider than 32 columns: the tree is expanded ONCE by the best-shaped kernel (16
+     * columns, NV = 4), which also caches each leaf's low word; every other column is produced by
+     * MAC-only passes over that cache.  Without the cache (disabled, lane-split batches, or a cache
+     * larger than the cap) wide entries fall back to one tree expansion per 64 columns. */
+    const size_t cache_bytes_est = (size_t)((nkeys + 31) / 32) * 32u * (size_t)c->n_local * sizeof(uint32_t);
+    const bool want_cache = mode_main == MODE_FUSED && c->entry_pad > 32 && nkeys >= 17 &&
+                            env_int("B200DPF_LEAF_CACHE", 1) != 0 &&
+                            cache_bytes_est <= ((size_t)env_int("B200DPF_LEAF_CACHE_MB", 16384) << 20);
+    const int nv = (mode_main != MODE_FUSED || c->entry_pad <= 16 || want_cache) ? 4 : (c->entry_pad <= 32 ? 8 : 16);
+    const int passes = mode_main == MODE_FUSED ? (want_cache ? 1 : c->entry_pad / (4 * nv)) : 1;
     SmemLayout L;
     int rc = smem_layout(c, prf, nv, mode_main, &L);
     if (rc) return rc;
@@ -311,22 +319,17 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         return B200DPF_OK;
     }
     p.out = reinterpret_cast<uint32_t *>(out_dev);
-    /* Wide entries (more than one 64-column pass): the first pass stores each leaf's low word
-     * (4 bytes x keys x leaves, coalesced), the remaining column blocks are MAC-only streaming
-     * passes over that cache instead of fresh tree expansions. */
     const size_t cache_bytes = (size_t)key_groups * 32u * (size_t)c->n_local * sizeof(uint32_t);
-    const bool use_cache = passes > 1 && nv == 16 && kpw_log2 == 5 && env_int("B200DPF_LEAF_CACHE", 1) != 0 &&
-                           cache_bytes <= ((size_t)env_int("B200DPF_LEAF_CACHE_MB", 16384) << 20);
-    if (use_cache) {
+    if (want_cache && kpw_log2 == 5) {
         rc = ensure_buffer(&c->d_leaf_cache, &c->leaf_cache_cap, cache_bytes);
         if (rc) return rc;
         p.leaf_cache = reinterpret_cast<uint32_t *>(c->d_leaf_cache);
         p.n_local = (uint64_t)c->n_local;
         p.col_off_v = 0;
         p.col_off = 0;
-        p.ncols = (uint32_t)std::min(64, c->entry_size);
+        p.ncols = (uint32_t)std::min(16, c->entry_size);
         p.counters = c->d_counters;
-        CUDA_TRY(launch_eval(prf, nv, MODE_FUSED, p, L.grid, smem, stream));
+        CUDA_TRY(launch_eval(prf, 4, MODE_FUSED, p, L.grid, smem, stream));
         c->last_launches++;
         MacParams m;
         std::memset(&m, 0, sizeof m);
@@ -338,21 +341,33 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         m.nkeys = (int)nkeys;
         m.key_groups = (int)key_groups;
         m.n_local = (uint64_t)c->n_local;
-        const int mac_grid = c->sm_count * 2;                      /* 2 blocks x 8 warps per SM */
+        const bool use_tma = env_int("B200DPF_MAC_TMA", 1) != 0;
+        const int mac_grid = c->sm_count * 2;                      /* register-staged variant */
         const int64_t mac_warps = (int64_t)mac_grid * 8;
         int64_t ranges = std::max<int64_t>(1, (2 * mac_warps + key_groups - 1) / key_groups);
         ranges = std::min<int64_t>(ranges, std::max<int64_t>(1, c->n_local / 64));
-        m.ranges_per_group = (uint32_t)ranges;
-        for (int pass = 1; pass < passes; pass++) {
-            m.col_off_v = (uint32_t)(pass * nv);
-            m.col_off = (uint32_t)(pass * 4 * nv);
-            m.ncols = (uint32_t)std::max(0, std::min(4 * nv, c->entry_size - pass * 4 * nv));
-            if (m.ncols == 0) break;
-            CUDA_TRY(launch_mac(nv, m, mac_grid, stream));
+        /* TMA variant: one block per SM; a block takes 8 key groups x one position range */
+        const int64_t kg_blocks = (key_groups + 7) / 8;
+        int64_t tr = std::max<int64_t>(1, (2 * (int64_t)c->sm_count + kg_blocks - 1) / kg_blocks);
+        tr = std::min<int64_t>(tr, std::max<int64_t>(1, c->n_local / 256));
+        for (int blk = 0; blk * 64 < c->entry_size; blk++) {       /* 64-column slices of the rows */
+            m.col_off_v = (uint32_t)(blk * 16);
+            m.col_off = (uint32_t)(blk * 64);
+            m.ncols = (uint32_t)std::min(64, c->entry_size - blk * 64);
+            m.col_skip = blk == 0 ? 16u : 0u;                      /* columns 0..15 came from the fused pass */
+            if (m.ncols <= m.col_skip) continue;
+            if (use_tma) {
+                m.ranges_per_group = (uint32_t)tr;
+                CUDA_TRY(launch_mac_tma(m, c->sm_count, stream));
+            } else {
+                m.ranges_per_group = (uint32_t)ranges;
+                CUDA_TRY(launch_mac(16, m, mac_grid, stream));
+            }
             c->last_launches++;
         }
         return B200DPF_OK;
     }
+    if (want_cache) return fail(B200DPF_ESTATE, "internal: leaf cache planned for a lane-split batch");
     for (int pass = 0; pass < passes; pass++) {
         p.col_off_v = (uint32_t)(pass * nv);
         p.col_off = (uint32_t)(pass * 4 * nv);

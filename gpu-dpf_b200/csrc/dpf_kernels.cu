@@ -140,7 +140,7 @@ struct DevEnv {
     __device__ __forceinline__ void leaf_pair(uint32_t local_pos, uint32_t v0, uint32_t v1)
     {
         if (MODE == MODE_FUSED) {
-            if (NV == 16 && leaf_out != nullptr) {   /* coalesced: 32 keys x 4 bytes per leaf */
+            if (leaf_out != nullptr) {   /* coalesced: 32 keys x 4 bytes per leaf */
                 leaf_out[(size_t)local_pos * 32] = v0;
                 leaf_out[(size_t)(local_pos + 1) * 32] = v1;
             }
@@ -378,7 +378,140 @@ __global__ void __launch_bounds__(256, 2) dpf_mac_kernel(const __grid_constant__
             uint32_t *o = p.out + (size_t)key * p.out_stride + p.col_off;
 #pragma unroll
             for (int e = 0; e < 4 * NV; e++)
-                if ((uint32_t)e < p.ncols) atomicAdd(o + e, acc[e]);
+                if ((uint32_t)e >= p.col_skip && (uint32_t)e < p.ncols) atomicAdd(o + e, acc[e]);
+        }
+    }
+}
+
+/* ---- TMA-staged MAC pass ---------------------------------------------------------------------
+ * Same arithmetic as dpf_mac_kernel, organised as a producer/consumer pipeline: one warp issues
+ * cp.async.bulk copies (table-row slices and cached leaves, global -> shared, completion counted
+ * on an mbarrier), eight consumer warps -- one key group each, all on the SAME leaf positions,
+ * so a row slice staged once is multiplied against 8 x 32 keys -- do LDS + IMAD only.  The
+ * register-staged variant above is latency bound (16 dependent load phases per trip); this one
+ * is bound by the FMA pipe. */
+namespace tma {
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 28)) __trap();   /* a lost arrival must not hang the GPU */
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+}  // namespace tma
+
+template <int NV>
+struct MacTmaShape {
+    enum { P = 32, STAGES = 3, GROUPS = 8, ROW_BYTES = NV * 16, LEAF_TILE = P * 128,
+           STAGE_BYTES = GROUPS * LEAF_TILE + P * ROW_BYTES, SMEM = STAGES * STAGE_BYTES + 64,
+           THREADS = (GROUPS + 1) * 32 };
+};
+
+template <int NV>
+__global__ void __launch_bounds__(MacTmaShape<NV>::THREADS, 1) dpf_mac_tma_kernel(const __grid_constant__ MacParams p)
+{
+    typedef MacTmaShape<NV> S;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(g_dyn_smem);
+    const uint32_t bars = smem0 + S::STAGES * S::STAGE_BYTES;   /* full[STAGES], empty[STAGES] */
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < S::STAGES; i++) {
+            tma::mbar_init(bars + 8 * i, 1);                       /* producer's expect_tx arrival */
+            tma::mbar_init(bars + 8 * (S::STAGES + i), S::GROUPS); /* one arrival per consumer warp */
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t kg_blocks = ((uint32_t)p.key_groups + S::GROUPS - 1) / S::GROUPS;
+    const uint64_t items = (uint64_t)kg_blocks * p.ranges_per_group;
+    const uint64_t len = (p.n_local + p.ranges_per_group - 1) / p.ranges_per_group;
+    uint32_t seq = 0;   /* tiles issued / consumed so far: stage = seq % STAGES, phase = (seq / STAGES) & 1 */
+
+    for (uint64_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const uint32_t kgb = (uint32_t)(it / p.ranges_per_group);
+        const uint32_t r = (uint32_t)(it - (uint64_t)kgb * p.ranges_per_group);
+        const uint64_t begin = (uint64_t)r * len;
+        const uint64_t end = begin + len < p.n_local ? begin + len : p.n_local;
+        const uint32_t kg0 = kgb * S::GROUPS;
+        const uint32_t ngroups = min((uint32_t)S::GROUPS, (uint32_t)p.key_groups - kg0);
+
+        if (warp == S::GROUPS) {
+            /* ===== producer warp ===== */
+            for (uint64_t pos = begin; pos < end; pos += S::P, seq++) {
+                const uint32_t stage = seq % S::STAGES, phase = (seq / S::STAGES) & 1u;
+                const uint32_t cnt = (uint32_t)min((uint64_t)S::P, end - pos);
+                const uint32_t sbase = smem0 + stage * S::STAGE_BYTES;
+                const uint32_t full = bars + 8 * stage, empty = bars + 8 * (S::STAGES + stage);
+                tma::mbar_wait(empty, phase ^ 1u);     /* consumers have released this stage */
+                if (lane == 0) tma::mbar_expect_tx(full, cnt * (128u * ngroups + S::ROW_BYTES));
+                __syncwarp();
+                if ((uint32_t)lane < ngroups)          /* cached leaves: one contiguous slab per key group */
+                    tma::bulk_g2s(sbase + lane * S::LEAF_TILE,
+                                  p.leaf_cache + ((size_t)(kg0 + lane) * p.n_local + pos) * 32, cnt * 128u, full);
+                for (uint32_t i = lane; i < cnt; i += 32)   /* one row slice per leaf position */
+                    tma::bulk_g2s(sbase + S::GROUPS * S::LEAF_TILE + i * S::ROW_BYTES,
+                                  p.table + (pos + i) * p.row_stride_v + p.col_off_v, S::ROW_BYTES, full);
+            }
+        } else {
+            /* ===== consumer warps: warp w = key group kg0 + w ===== */
+            const bool active = (uint32_t)warp < ngroups;
+            uint32_t acc[4 * NV];
+#pragma unroll
+            for (int e = 0; e < 4 * NV; e++) acc[e] = 0;
+            for (uint64_t pos = begin; pos < end; pos += S::P, seq++) {
+                const uint32_t stage = seq % S::STAGES, phase = (seq / S::STAGES) & 1u;
+                const uint32_t cnt = (uint32_t)min((uint64_t)S::P, end - pos);
+                const unsigned char *sbase = g_dyn_smem + stage * S::STAGE_BYTES;
+                tma::mbar_wait(bars + 8 * stage, phase);   /* the bytes have landed */
+                if (active) {
+                    const uint32_t *leaf = reinterpret_cast<const uint32_t *>(sbase + warp * S::LEAF_TILE) + lane;
+                    const uint4 *rows = reinterpret_cast<const uint4 *>(sbase + S::GROUPS * S::LEAF_TILE);
+#pragma unroll 2
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        const uint32_t v = leaf[i * 32];
+#pragma unroll
+                        for (int j = 0; j < NV; j++) {
+                            const uint4 t = rows[i * NV + j];
+                            acc[4 * j + 0] += v * t.x;
+                            acc[4 * j + 1] += v * t.y;
+                            acc[4 * j + 2] += v * t.z;
+                            acc[4 * j + 3] += v * t.w;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(bars + 8 * (S::STAGES + stage));
+            }
+            const int key = (int)(kg0 + warp) * 32 + lane;
+            if (active && key < p.nkeys) {
+                uint32_t *o = p.out + (size_t)key * p.out_stride + p.col_off;
+#pragma unroll
+                for (int e = 0; e < 4 * NV; e++)
+                    if ((uint32_t)e >= p.col_skip && (uint32_t)e < p.ncols) atomicAdd(o + e, acc[e]);
+            }
         }
     }
 }
@@ -510,6 +643,16 @@ cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes)
     case PRF_AES128: return max_smem_prf<PRF_AES128>(nv, mode, bytes);
     default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_mac_tma(const MacParams &p, int grid, cudaStream_t stream)
+{
+    typedef MacTmaShape<16> S;
+    auto kern = dpf_mac_tma_kernel<16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, (int)S::THREADS, (int)S::SMEM, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mac(int nv, const MacParams &p, int grid, cudaStream_t stream)

@@ -88,11 +88,15 @@ struct MacParams {
     uint32_t row_stride_v, col_off_v;
     uint32_t *out;
     uint32_t out_stride, col_off, ncols;
+    uint32_t col_skip;            /* leading columns of the slice that another pass already produced */
     int nkeys, key_groups;
     uint64_t n_local;
     uint32_t ranges_per_group;    /* position ranges a key group is cut into (one warp each) */
 };
 cudaError_t launch_mac(int nv, const MacParams &p, int grid, cudaStream_t stream);
+/* Same pass (64 columns) with the operands staged into shared memory by cp.async.bulk
+ * (TMA) under mbarriers: 8 key groups per block share every staged row slice. */
+cudaError_t launch_mac_tma(const MacParams &p, int grid, cudaStream_t stream);
 
 /* Maximum dynamic shared memory the evaluation kernel may be given. */
 cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes);
