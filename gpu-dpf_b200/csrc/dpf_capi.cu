@@ -68,7 +68,10 @@ struct DeviceGuard {
 
 }  // namespace
 
+struct SmemLayoutCache;   /* per (prf, nv, mode) launch layouts, filled on first use */
+
 struct b200dpf_ctx {
+    SmemLayoutCache *layouts = nullptr;
     int device = 0;
     int64_t n = 0;
     int depth = 0;
@@ -104,8 +107,36 @@ struct SmemLayout {
     int cap_lo, cap_hi, s_max;
 };
 
-/* Dynamic shared memory layout of the kernel instantiated for (prf, nv, mode). */
+}  // namespace
+
+struct SmemLayoutCache {
+    SmemLayout entry[4][3][3];
+    bool valid[4][3][3] = {};
+};
+
+namespace {
+
+int smem_layout_compute(b200dpf_ctx *c, int prf, int nv, int mode, SmemLayout *L);
+
+/* Dynamic shared memory layout of the kernel instantiated for (prf, nv, mode); the CUDA
+ * attribute queries behind it are made once per context. */
 int smem_layout(b200dpf_ctx *c, int prf, int nv, int mode, SmemLayout *L)
+{
+    const int ni = nv == 4 ? 0 : (nv == 8 ? 1 : 2);
+    if (!c->layouts) c->layouts = new (std::nothrow) SmemLayoutCache();
+    if (c->layouts && c->layouts->valid[prf][ni][mode]) {
+        *L = c->layouts->entry[prf][ni][mode];
+        return B200DPF_OK;
+    }
+    const int rc = smem_layout_compute(c, prf, nv, mode, L);
+    if (rc == B200DPF_OK && c->layouts) {
+        c->layouts->entry[prf][ni][mode] = *L;
+        c->layouts->valid[prf][ni][mode] = true;
+    }
+    return rc;
+}
+
+int smem_layout_compute(b200dpf_ctx *c, int prf, int nv, int mode, SmemLayout *L)
 {
     std::memset(L, 0, sizeof *L);
     L->threads = eval_threads(prf, nv);
@@ -561,6 +592,7 @@ int b200dpf_destroy(b200dpf_ctx *c)
     if (c->d_frontier) cudaFree(c->d_frontier);
     if (c->d_leaf_cache) cudaFree(c->d_leaf_cache);
     if (c->stream) cudaStreamDestroy(c->stream);
+    delete c->layouts;
     delete c;
     return B200DPF_OK;
 }
