@@ -92,6 +92,10 @@ struct b200dpf_ctx {
     size_t frontier_cap = 0;  /* bytes */
     void *d_leaf_cache = nullptr;
     size_t leaf_cache_cap = 0;  /* bytes */
+    int32_t *h_keys = nullptr;  /* pinned staging */
+    size_t h_keys_cap = 0;      /* keys */
+    int32_t *h_out = nullptr;   /* pinned staging */
+    size_t h_out_cap = 0;       /* int32 elements */
     int sm_count = 0;
     uint32_t smem_base = 0;
     int s_override = 0;
@@ -416,6 +420,26 @@ int run_eval(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void 
     return run_pipeline(c, keys_dev, nkeys, prf, MODE_FUSED, out_dev, stream);
 }
 
+bool is_pinned_host(const void *ptr)
+{
+    cudaPointerAttributes attr;
+    const bool yes = cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return yes;
+}
+
+int ensure_host_keys(b200dpf_ctx *c, int64_t nkeys)
+{
+    if ((size_t)nkeys <= c->h_keys_cap) return B200DPF_OK;
+    if (c->h_keys) cudaFreeHost(c->h_keys);
+    c->h_keys = nullptr;
+    c->h_keys_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)nkeys, 512);
+    CUDA_TRY(cudaMallocHost(&c->h_keys, cap * host::KEY_WORDS * sizeof(int32_t)));
+    c->h_keys_cap = cap;
+    return B200DPF_OK;
+}
+
 int check_eval_args(const b200dpf_ctx *c, const void *keys, int64_t nkeys, int prf, const void *out)
 {
     if (!c) return fail(B200DPF_EINVAL, "null context");
@@ -591,6 +615,8 @@ int b200dpf_destroy(b200dpf_ctx *c)
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_frontier) cudaFree(c->d_frontier);
     if (c->d_leaf_cache) cudaFree(c->d_leaf_cache);
+    if (c->h_keys) cudaFreeHost(c->h_keys);
+    if (c->h_out) cudaFreeHost(c->h_out);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c->layouts;
     delete c;
@@ -622,12 +648,45 @@ int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, in
         CUDA_TRY(cudaMalloc(&c->d_out, out_elems * sizeof(int32_t)));
         c->out_cap = out_elems;
     }
-    CUDA_TRY(cudaMemcpyAsync(c->d_keys, keys, (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t),
-                             cudaMemcpyHostToDevice, c->stream));
+    /* pageable host memory goes through the context's pinned staging so both copies are real
+     * asynchronous DMA transfers; already-pinned buffers (ours or the caller's) are used as is */
+    const size_t key_bytes = (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t);
+    const int32_t *src = keys;
+    if (!is_pinned_host(keys)) {
+        rc = ensure_host_keys(c, nkeys);
+        if (rc) return rc;
+        std::memcpy(c->h_keys, keys, key_bytes);
+        src = c->h_keys;
+    }
+    int32_t *dst = out;
+    if (!is_pinned_host(out)) {
+        if (out_elems > c->h_out_cap) {
+            if (c->h_out) cudaFreeHost(c->h_out);
+            c->h_out = nullptr;
+            c->h_out_cap = 0;
+            const size_t cap = std::max<size_t>(out_elems, 8192);
+            CUDA_TRY(cudaMallocHost(&c->h_out, cap * sizeof(int32_t)));
+            c->h_out_cap = cap;
+        }
+        dst = c->h_out;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_keys, src, key_bytes, cudaMemcpyHostToDevice, c->stream));
     rc = run_eval(c, c->d_keys, nkeys, prf, c->d_out, c->stream);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (dst != out) std::memcpy(out, dst, out_elems * sizeof(int32_t));
+    return B200DPF_OK;
+}
+
+int b200dpf_host_staging(b200dpf_ctx *c, int64_t nkeys, int32_t **keys_pinned)
+{
+    if (!c || !keys_pinned || nkeys < 1) return fail(B200DPF_EINVAL, "bad host_staging argument");
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    const int rc = ensure_host_keys(c, nkeys);
+    if (rc) return rc;
+    *keys_pinned = c->h_keys;
     return B200DPF_OK;
 }
 

@@ -145,12 +145,13 @@ at::Tensor eval_gpu_list(const std::vector<at::Tensor> &keys, const std::vector<
     const int64_t esz = b200dpf_ctx_entry_size(ctx);
     at::Tensor result = torch::empty({total, esz}, at::kInt);
     if (total == 0) return result;
-    std::vector<int32_t> packed((size_t)total * kKeyWords);
+    int32_t *packed = nullptr;   /* the context's pinned staging: packed once, DMA'd from there */
+    check(b200dpf_host_staging(ctx, total, &packed), "eval_gpu");
     for (int64_t i = 0; i < total; i++)
-        std::memcpy(packed.data() + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
+        std::memcpy(packed + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
     {
         py::gil_scoped_release nogil;
-        check(b200dpf_eval(ctx, packed.data(), total, prf, result.data_ptr<int32_t>()), "eval_gpu");
+        check(b200dpf_eval(ctx, packed, total, prf, result.data_ptr<int32_t>()), "eval_gpu");
     }
     return result;
 }
@@ -167,14 +168,15 @@ at::Tensor eval_gpu(const std::vector<at::Tensor> &keys, const std::vector<void 
     int64_t unique = total;
     while (unique > 1 && keys[(size_t)unique - 1].unsafeGetTensorImpl() == keys[(size_t)unique - 2].unsafeGetTensorImpl()) unique--;
     const int64_t esz = b200dpf_ctx_entry_size(ctx);
-    std::vector<int32_t> packed((size_t)unique * kKeyWords);
+    int32_t *packed = nullptr;
+    check(b200dpf_host_staging(ctx, unique, &packed), "eval_gpu");
     for (int64_t i = 0; i < unique; i++)
-        std::memcpy(packed.data() + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
+        std::memcpy(packed + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
     at::Tensor result = torch::empty({total, esz}, at::kInt);
     int32_t *r = result.data_ptr<int32_t>();
     {
         py::gil_scoped_release nogil;
-        check(b200dpf_eval(ctx, packed.data(), unique, prf, r), "eval_gpu");
+        check(b200dpf_eval(ctx, packed, unique, prf, r), "eval_gpu");
     }
     for (int64_t i = unique; i < total; i++) std::memcpy(r + i * esz, r + (unique - 1) * esz, sizeof(int32_t) * (size_t)esz);
     return result;

@@ -148,6 +148,15 @@ int b200dpf_destroy(b200dpf_ctx *ctx);
 int b200dpf_eval(b200dpf_ctx *ctx, const int32_t *keys, int64_t nkeys, int prf, int32_t *out);
 
 /*
+ * Pinned (page-locked) host staging owned by the context, sized for `nkeys` keys: callers
+ * that assemble a batch from scattered keys (the reference passes 512 separate tensors,
+ * dpf_wrapper.cu:137-146) can pack straight into it and hand the same pointer to
+ * b200dpf_eval, which then copies to the device without an intermediate staging copy.
+ * The buffer stays valid until the next b200dpf_host_staging / b200dpf_destroy.
+ */
+int b200dpf_host_staging(b200dpf_ctx *ctx, int64_t nkeys, int32_t **keys_pinned);
+
+/*
  * Same computation with DEVICE buffers, enqueued on `cuda_stream` (a
  * cudaStream_t, may be NULL for the default stream) and NOT synchronised:
  * for callers that keep keys and results resident (benchmarks, NCCL reduce of
