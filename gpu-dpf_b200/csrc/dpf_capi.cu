@@ -599,6 +599,26 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_stage);
     CTX_TRY(e);
+
+    /* Like the reference's eval_init (dpf_wrapper.cu:120-129), set up everything a default batch
+     * (512 keys) needs now, so the first evaluation pays neither allocations nor lazy module
+     * loading: device key/result/ticket buffers, pinned staging, launch layouts of every PRF. */
+    {
+        const int64_t b0 = B200DPF_DEFAULT_BATCH_SIZE;
+        CTX_TRY(cudaMalloc(&c->d_keys, (size_t)b0 * host::KEY_WORDS * sizeof(int32_t)));
+        c->keys_cap = (size_t)b0;
+        CTX_TRY(cudaMalloc(&c->d_out, (size_t)b0 * entry_size * sizeof(int32_t)));
+        c->out_cap = (size_t)b0 * entry_size;
+        if (ensure_host_keys(c, b0) != B200DPF_OK) { b200dpf_destroy(c); return B200DPF_ECUDA; }
+        CTX_TRY(cudaMallocHost(&c->h_out, std::max<size_t>((size_t)b0 * entry_size, 8192) * sizeof(int32_t)));
+        c->h_out_cap = std::max<size_t>((size_t)b0 * entry_size, 8192);
+        const int nv0 = c->entry_pad <= 16 ? 4 : (c->entry_pad <= 32 ? 8 : 4);
+        SmemLayout tmp;
+        for (int prf = 0; prf < 4; prf++) {
+            smem_layout(c, prf, nv0, MODE_FUSED, &tmp);
+            smem_layout(c, prf, 4, MODE_FRONTIER, &tmp);
+        }
+    }
 #undef CTX_TRY
     *out = c;
     return B200DPF_OK;
