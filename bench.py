@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--subtree-log2", type=int, default=0)
+    ap.add_argument("--strong", action="store_true",
+                    help="N>1: keep the GLOBAL batch at --batch-per-gpu keys (strong scaling: each GPU still sees "
+                         "every key but only 1/N of the leaves) instead of growing it with N")
     ap.add_argument("--reduce", default="nccl", choices=["nccl", "fused"],
                     help="N>1: NCCL reduce of the partials, or the kernel's peer-memory red.add epilogue")
     return ap.parse_args()
@@ -279,7 +282,7 @@ def run_ours(args):
 
     prf = PRF_IDS[args.prf]
     n, entry = args.n, args.entry
-    batch = args.batch_per_gpu * world
+    batch = args.batch_per_gpu * (1 if args.strong else world)
     table = synthetic_table(n, entry)
     keys_np, _ = synthetic_keys(n, batch, prf)
 
@@ -417,10 +420,12 @@ def run_ours(args):
         line = {
             "metric": "DPFs/sec", "value": value, "unit": "DPFs/sec", "n_gpus": world, "steps": args.steps,
             "warmup": nwarm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": (value / published) if published else None, "dtype": "u32",
+            "scaling": "strong" if args.strong else "weak",
+            "vs_baseline": (value / published) if published else None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": "n=%d entry_size=%d %s batch=%d (512 per GPU), table entry-range sharded over %d GPU(s)"
-                                   % (n, entry, args.prf.upper(), batch, world),
+            "config": {"workload": "n=%d entry_size=%d %s batch=%d (%s), table entry-range sharded over %d GPU(s)"
+                                   % (n, entry, args.prf.upper(), batch,
+                                      "fixed global batch" if args.strong else "%d per GPU" % args.batch_per_gpu, world),
                        "n": n, "entry_size": entry, "prf": args.prf.upper(), "global_batch": batch,
                        "parallelism": ("entry-shard x%d + %s" % (world, "NCCL reduce" if args.reduce == "nccl" else
                                        "in-kernel peer-memory red.add (symmetric memory)")) if world > 1 else "single GPU",
