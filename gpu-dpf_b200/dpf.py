@@ -56,7 +56,11 @@ class DPF(object):
         dpf_cpp.PRF_AES128: "AES128",
     }
 
-    def __init__(self, prf=None, device=0, shard=(0, 1)):
+    def __init__(self, prf=None, device=0, shard=(0, 1), allow_non_pow2=False):
+        # allow_non_pow2: tables / domains whose size is not a power of two are padded with zero
+        # rows up to the next one (a reference TODO, dpf.py:21; off by default so the reference's
+        # "must be a power of two" errors stay as they are)
+        self.allow_non_pow2 = allow_non_pow2
         self.buffers = None
         self.table_num_entries = None
         self.table_effective_entry_size = None
@@ -73,11 +77,12 @@ class DPF(object):
         reference's generator only consumes 32 bits of it, dpf_wrapper.cu:52)."""
         if seed is None:
             seed = os.urandom(128)
-        if n & (n - 1) != 0:
+        if n & (n - 1) != 0 and not self.allow_non_pow2:
             raise Exception("Table num entries (%d) must be a power of two" % (n))
         if k >= n:
             raise Exception("k (%d), the selected element, must be less than n (%d), the number of entries in the table"
                             % (k, n))
+        n = _next_pow2(n)
         if secure:
             return dpf_cpp.gen_secure(k, n, seed, self.prf_method)
         return dpf_cpp.gen(k, n, seed, self.prf_method)
@@ -106,16 +111,18 @@ class DPF(object):
 
     def eval_init(self, table):
         """Upload the table (dpf.py:88-113).  Any entry size; no column padding."""
-        self.table = table
         if self.buffers is not None:
             dpf_cpp.eval_free(self.buffers)
             self.buffers = None
+        if table.shape[0] < 128:
+            raise Exception("Table (%d) must have at least 128 elements" % table.shape[0])
+        if table.shape[0] & (table.shape[0] - 1) != 0:
+            if not self.allow_non_pow2:
+                raise Exception("Table num entries (%d) must be a power of two" % (table.shape[0]))
+            table = _pad_rows_to_pow2(table)
+        self.table = table
         self.table_num_entries = table.shape[0]
         self.table_effective_entry_size = table.shape[1]
-        if self.table_num_entries < 128:
-            raise Exception("Table (%d) must have at least 128 elements" % self.table_num_entries)
-        if self.table_num_entries & (self.table_num_entries - 1) != 0:
-            raise Exception("Table num entries (%d) must be a power of two" % (self.table_num_entries))
         self.buffers = dpf_cpp.eval_init_sharded(table, self.device, self.shard[0], self.shard[1])
 
     def eval_gpu(self, keys):
@@ -212,6 +219,16 @@ class DPF(object):
             return "DPF(_uninitialized_, prf_method=%s)" % self.prf_method_string
         return "DPF(entries=%d, entry_size=%d, prf_method=%s)" % (
             self.table_num_entries, self.table_effective_entry_size, self.prf_method_string)
+
+
+def _next_pow2(n):
+    return 1 << max(1, (n - 1).bit_length())
+
+
+def _pad_rows_to_pow2(table):
+    """Zero rows up to the next power of two: they contribute nothing to any inner product."""
+    pad = _next_pow2(table.shape[0]) - table.shape[0]
+    return torch.cat([table, torch.zeros((pad, table.shape[1]), dtype=table.dtype)])
 
 
 # ---------------------------------------------------------------------------

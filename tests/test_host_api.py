@@ -131,6 +131,22 @@ def test_python_api_cpu_side():
     dpf.test_cpu_dpf()
 
 
+def test_non_power_of_two_domains_opt_in():
+    import dpf
+    d = dpf.DPF(prf=dpf.DPF.PRF_CHACHA20, allow_non_pow2=True)
+    n = 1000
+    table = torch.arange(n * 3, dtype=torch.int32).reshape(n, 3)
+    k1, k2 = d.gen(999, n)
+    assert int(k1.view(torch.int32)[130 * 4]) == 1024          # keys live in the padded domain
+    d.table = dpf._pad_rows_to_pow2(table)                      # what eval_init stores (no GPU needed here)
+    rec = d.eval_cpu([k1]) - d.eval_cpu([k2])
+    assert torch.equal(rec[0], table[999])
+    with pytest.raises(Exception, match="must be less than n"):
+        d.gen(1000, n)
+    with pytest.raises(Exception, match="power of two"):
+        dpf.DPF().gen(5, n)                                     # default: the reference's behaviour
+
+
 def test_python_gen_is_reference_compatible(golden):
     """dpf_cpp.gen(k, n, seed, prf) with the same first 4 seed bytes reproduces the
     reference's keys bit for bit (dpf_wrapper.cu:52 seeds mt19937 from them)."""
