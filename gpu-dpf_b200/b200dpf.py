@@ -19,7 +19,7 @@ PRF_NAMES = {0: "DUMMY", 1: "SALSA20", 2: "CHACHA20", 3: "AES128"}
 # every symbol include/b200dpf.h declares
 SYMBOLS = [
     "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_eval_cpu",
-    "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
+    "b200dpf_key_packed_size", "b200dpf_key_pack", "b200dpf_key_unpack", "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
     "b200dpf_host_staging", "b200dpf_eval_device", "b200dpf_eval_device_acc", "b200dpf_expand_device", "b200dpf_ctx_n", "b200dpf_ctx_entry_size",
     "b200dpf_ctx_device", "b200dpf_ctx_last_launches", "b200dpf_ctx_set_subtree_log2",
 ]
@@ -43,6 +43,10 @@ def load():
     L.b200dpf_gen_secure.argtypes = [C.c_int64, C.c_int64, C.c_char_p, C.c_size_t, C.c_int, _i32p, _i32p]
     L.b200dpf_gen_batch.argtypes = [_i64p, _u32p, C.c_int64, C.c_int64, C.c_int, C.c_int, _i32p, _i32p]
     L.b200dpf_eval_cpu.argtypes = [_i32p, C.c_int, _i32p]
+    L.b200dpf_key_packed_size.argtypes = [C.c_int]
+    L.b200dpf_key_packed_size.restype = C.c_size_t
+    L.b200dpf_key_pack.argtypes = [_i32p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.b200dpf_key_unpack.argtypes = [C.c_char_p, C.c_size_t, _i32p]
     L.b200dpf_key_n.argtypes = [_i32p]
     L.b200dpf_key_n.restype = C.c_int64
     L.b200dpf_key_depth.argtypes = [_i32p]
@@ -99,6 +103,20 @@ def gen_batch(alphas, n, seeds32, prf, nthreads=0):
     b = np.zeros((len(alphas), KEY_WORDS), np.int32)
     _check(lib().b200dpf_gen_batch(alphas, seeds32, len(alphas), n, prf, nthreads, a, b), "b200dpf_gen_batch")
     return a, b
+
+
+def key_pack(key):
+    key = np.ascontiguousarray(key, np.int32)
+    buf = C.create_string_buffer(lib().b200dpf_key_packed_size(32))
+    n = C.c_size_t()
+    _check(lib().b200dpf_key_pack(key, buf, len(buf), C.byref(n)), "b200dpf_key_pack")
+    return buf.raw[:n.value]
+
+
+def key_unpack(packed):
+    key = np.zeros(KEY_WORDS, np.int32)
+    _check(lib().b200dpf_key_unpack(bytes(packed), len(packed), key), "b200dpf_key_unpack")
+    return key
 
 
 def eval_cpu(key, prf):

@@ -509,6 +509,50 @@ int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n)
     return B200DPF_OK;
 }
 
+size_t b200dpf_key_packed_size(int depth) { return depth >= 1 && depth <= 32 ? (size_t)24 + 64u * (size_t)depth : 0; }
+
+int b200dpf_key_pack(const int32_t *key, uint8_t *out, size_t out_cap, size_t *written)
+{
+    if (!key || !out) return fail(B200DPF_EINVAL, "null buffer");
+    const int depth = host::key_depth(key);
+    if (depth < 1 || host::key_n(key) < 0) return fail(B200DPF_EINVAL, "key_pack: malformed key");
+    const size_t need = b200dpf_key_packed_size(depth);
+    if (out_cap < need) return fail(B200DPF_EINVAL, "key_pack: need %zu bytes, have %zu", need, out_cap);
+    const uint8_t *k = reinterpret_cast<const uint8_t *>(key);
+    std::memcpy(out, "DPF1", 4);
+    out[4] = (uint8_t)depth;
+    out[5] = out[6] = out[7] = 0;
+    std::memcpy(out + 8, k + 16 * host::SLOT_ROOT, 16);
+    for (int L = 0; L < depth; L++) {
+        uint8_t *o = out + 24 + 64 * L;
+        std::memcpy(o, k + 16 * (host::SLOT_CW1 + 2 * L), 32);
+        std::memcpy(o + 32, k + 16 * (host::SLOT_CW2 + 2 * L), 32);
+    }
+    if (written) *written = need;
+    return B200DPF_OK;
+}
+
+int b200dpf_key_unpack(const uint8_t *in, size_t in_len, int32_t *key)
+{
+    if (!in || !key) return fail(B200DPF_EINVAL, "null buffer");
+    if (in_len < 24 || std::memcmp(in, "DPF1", 4) != 0) return fail(B200DPF_EINVAL, "key_unpack: bad header");
+    const int depth = in[4];
+    if (depth < 1 || depth > 32 || in[5] || in[6] || in[7] || in_len != b200dpf_key_packed_size(depth))
+        return fail(B200DPF_EINVAL, "key_unpack: depth %d does not match %zu bytes", depth, in_len);
+    std::memset(key, 0, sizeof(int32_t) * host::KEY_WORDS);
+    uint8_t *k = reinterpret_cast<uint8_t *>(key);
+    k[16 * host::SLOT_DEPTH] = (uint8_t)depth;
+    std::memcpy(k + 16 * host::SLOT_ROOT, in + 8, 16);
+    for (int L = 0; L < depth; L++) {
+        const uint8_t *o = in + 24 + 64 * L;
+        std::memcpy(k + 16 * (host::SLOT_CW1 + 2 * L), o, 32);
+        std::memcpy(k + 16 * (host::SLOT_CW2 + 2 * L), o + 32, 32);
+    }
+    const uint64_t n = (uint64_t)1 << depth;
+    std::memcpy(k + 16 * host::SLOT_N, &n, 8);
+    return B200DPF_OK;
+}
+
 int64_t b200dpf_key_n(const int32_t *key) { return key ? host::key_n(key) : -1; }
 int b200dpf_key_depth(const int32_t *key) { return key ? host::key_depth(key) : -1; }
 

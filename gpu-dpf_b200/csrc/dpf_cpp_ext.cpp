@@ -69,6 +69,24 @@ std::vector<at::Tensor> gen_secure(int64_t k, int64_t n, const std::string &seed
     return {a, b};
 }
 
+/* compact wire form: int32[524] key tensor <-> bytes (24 + 64*depth) */
+py::bytes key_pack(const at::Tensor &key)
+{
+    const int32_t *k = key_ptr(key);
+    std::string buf(b200dpf_key_packed_size(32), '\0');
+    size_t written = 0;
+    check(b200dpf_key_pack(k, reinterpret_cast<uint8_t *>(&buf[0]), buf.size(), &written), "key_pack");
+    return py::bytes(buf.data(), written);
+}
+
+at::Tensor key_unpack(const std::string &packed)
+{
+    at::Tensor key = torch::zeros({kKeyWords}, at::kInt);
+    check(b200dpf_key_unpack(reinterpret_cast<const uint8_t *>(packed.data()), packed.size(), key.data_ptr<int32_t>()),
+          "key_unpack");
+    return key;
+}
+
 /* batched keygen: alphas int64[B], seeds int64[B] (low 32 bits used) -> two int32[B,524] tensors */
 std::vector<at::Tensor> gen_batch(const at::Tensor &alphas, int64_t n, const at::Tensor &seeds, int prf, int nthreads)
 {
@@ -228,6 +246,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     /* additions */
     m.attr("NATIVE_SHAPES") = py::int_(1);
     m.def("version", []() { return std::string(b200dpf_version()); });
+    m.def("key_pack", &key_pack, "compact wire form of a key (bytes)");
+    m.def("key_unpack", &key_unpack, "restore an int32[524] key from its compact form");
     m.def("gen_secure", &gen_secure, "dpf gen from a ChaCha20 DRBG (seed: >= 44 bytes)");
     m.def("gen_batch", &gen_batch, "batched multi-threaded keygen", py::arg("alphas"), py::arg("n"), py::arg("seeds"),
           py::arg("prf"), py::arg("nthreads") = 0);

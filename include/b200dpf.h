@@ -107,6 +107,19 @@ int b200dpf_gen_batch(const int64_t *alphas, const uint32_t *seeds32, int64_t co
  */
 int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n);
 
+/*
+ * Compact wire form of a key.  Of the 131 slots of the
+ * reference format only 4*depth correction words, the root seed and the depth are live
+ * (dpf_base/dpf.h:18-29 sizes the arrays for n = 2^32).  Packed layout, little endian:
+ *   "DPF1" | depth (u8) | 3 zero bytes | root seed (16) | per level L = 0..depth-1:
+ *   cw_1[2L], cw_1[2L+1], cw_2[2L], cw_2[2L+1] (16 bytes each)
+ * = 24 + 64*depth bytes (1304 at n = 2^20 instead of 2096).  unpack() restores the exact
+ * int32[524] key (unused slots zero), so packed keys evaluate bit-identically.
+ */
+size_t b200dpf_key_packed_size(int depth);
+int b200dpf_key_pack(const int32_t *key, uint8_t *out, size_t out_cap, size_t *written);
+int b200dpf_key_unpack(const uint8_t *in, size_t in_len, int32_t *key);
+
 /* n stored in a key (slot 130) and its depth (slot 0); -1 if malformed. */
 int64_t b200dpf_key_n(const int32_t *key);
 int b200dpf_key_depth(const int32_t *key);

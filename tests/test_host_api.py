@@ -131,6 +131,27 @@ def test_python_api_cpu_side():
     dpf.test_cpu_dpf()
 
 
+def test_compact_key_format(golden):
+    """pack/unpack round-trips every golden key exactly and shrinks it to 24 + 64*depth bytes."""
+    import dpf_cpp
+    for ci, (prf, n, alpha, seed32) in enumerate(golden["case_meta"]):
+        for keys in (golden["keys_a"], golden["keys_b"]):
+            k = keys[ci]
+            packed = b200dpf.key_pack(k)
+            depth = int(n).bit_length() - 1
+            assert len(packed) == 24 + 64 * depth and packed[:4] == b"DPF1"
+            assert np.array_equal(b200dpf.key_unpack(packed), k)
+    k = torch.from_numpy(golden["keys_a"][5].copy())
+    assert torch.equal(dpf_cpp.key_unpack(dpf_cpp.key_pack(k)), k)
+    with pytest.raises(b200dpf.B200DPFError, match="bad header"):
+        b200dpf.key_unpack(b"XXXX" + bytes(100))
+    good = b200dpf.key_pack(golden["keys_a"][5])
+    with pytest.raises(b200dpf.B200DPFError, match="does not match"):
+        b200dpf.key_unpack(good[:-1])
+    with pytest.raises(b200dpf.B200DPFError, match="malformed"):
+        b200dpf.key_pack(np.zeros(524, np.int32))
+
+
 def test_non_power_of_two_domains_opt_in():
     import dpf
     d = dpf.DPF(prf=dpf.DPF.PRF_CHACHA20, allow_non_pow2=True)
