@@ -57,10 +57,7 @@ def key_slice(nkeys, rank, world):
 class ShardedDPF(object):
     """dpf.DPF semantics over a process group; rank 0 receives the result."""
 
-    def __init__(self, prf=None, group=None, device=None, axis="entries", reduce="nccl", partial_fn=None):
-        # partial_fn(keys_packed_cpu_int32[B,524]) -> int32 [B,E] tensor of this rank's
-        # contribution.  Default: the CUDA engine.  Tests inject a CPU stand-in to exercise the
-        # process-group plumbing with the gloo backend.
+    def __init__(self, prf=None, group=None, device=None, axis="entries", reduce="nccl"):
         assert axis in ("entries", "keys") and reduce in ("nccl", "fused")
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -70,7 +67,6 @@ class ShardedDPF(object):
         self.device = int(os.environ.get("LOCAL_RANK", self.rank)) if device is None else device
         self.axis = axis
         self.reduce = reduce if self.world > 1 else "nccl"
-        self._partial_fn = partial_fn
         self._dpf = None
         self.prf = prf
         self.entry_size = None
@@ -79,11 +75,10 @@ class ShardedDPF(object):
 
     def eval_init(self, table):
         self.n, self.entry_size = table.shape[0], table.shape[1]
-        if self._partial_fn is None:
-            import dpf
-            shard = (self.rank, self.world) if self.axis == "entries" else (0, 1)
-            self._dpf = dpf.DPF(prf=self.prf, device=self.device, shard=shard)
-            self._dpf.eval_init(table)
+        import dpf
+        shard = (self.rank, self.world) if self.axis == "entries" else (0, 1)
+        self._dpf = dpf.DPF(prf=self.prf, device=self.device, shard=shard)
+        self._dpf.eval_init(table)
         return self
 
     # -- fused reduction plumbing ------------------------------------------------
@@ -127,9 +122,7 @@ class ShardedDPF(object):
             hdl.barrier(channel=1)                 # every rank's adds have landed
             return view
         out_dev = self._dpf.eval_gpu_device(keys_dev, out_dev)
-        if self.world > 1:
-            dist.reduce(out_dev, dst=0, op=dist.ReduceOp.SUM, group=self.group)
-        return out_dev
+        return self._reduce_to_rank0(out_dev)
 
     # -- host-buffer path (the dpf.DPF.eval_gpu contract) --
     def eval_gpu(self, keys):
@@ -137,18 +130,24 @@ class ShardedDPF(object):
             packed = keys.contiguous()
         else:
             packed = torch.stack(list(keys))
-        if self._partial_fn is not None:
-            part = self._partial_fn(packed)
-            if self.world > 1:
-                dist.reduce(part, dst=0, op=dist.ReduceOp.SUM, group=self.group)
-            return part.cpu() if self.rank == 0 else None
+        out = self._evaluate_and_combine(packed)
+        return out.cpu() if self.rank == 0 else None
+
+    def _evaluate_and_combine(self, packed):
+        """This rank's evaluation on its GPU plus the cross-rank step; the tensor returned on
+        rank 0 holds the complete result.  (The seam the CPU process-group tests override.)"""
         dev = torch.device("cuda", self.device)
         keys_dev = packed.to(dev, non_blocking=True)
         out_dev = self.eval_gpu_device(keys_dev)
-        if self.rank == 0:
-            return out_dev.cpu()
-        torch.cuda.current_stream(dev).synchronize()
-        return None
+        if self.rank != 0:
+            torch.cuda.current_stream(dev).synchronize()
+        return out_dev
+
+    def _reduce_to_rank0(self, part):
+        """Wrapping int32 sum of the per-shard partials onto rank 0."""
+        if self.world > 1:
+            dist.reduce(part, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+        return part
 
     def close(self):
         if self._dpf is not None:

@@ -1,7 +1,7 @@
 """Host-side logic of the multi-GPU path on CPU: world_size-2 (and 4) process groups over
-gloo.  The per-rank partial is supplied by the oracle (a test stand-in injected through
-ShardedDPF's partial_fn hook); what is under test is the product's shard index math,
-process-group plumbing and the int32 wrapping reduce."""
+gloo.  There is no GPU here, so a TEST subclass of ShardedDPF replaces the per-rank GPU
+evaluation with the oracle's shard partial; what is under test is the product's shard index
+math, process-group plumbing and the int32 wrapping reduce (ShardedDPF._reduce_to_rank0)."""
 import os
 import socket
 import sys
@@ -41,11 +41,17 @@ def _worker(rank, world, port, n, prf, ret):
     depth = n.bit_length() - 1
     assert rows == [orc.bitrev(rank * (n // world) + q, depth) for q in range(n // world)]
 
-    def partial(packed):
-        out = np.stack([orc.eval_dot_shard(k, prf, table, rank * (n // world), n // world) for k in packed.numpy()])
-        return torch.from_numpy(out)
+    class OracleBackedShards(ShardedDPF):
+        def eval_init(self, t):
+            self.n, self.entry_size = t.shape
+            return self
 
-    d = ShardedDPF(prf=prf, partial_fn=partial)
+        def _evaluate_and_combine(self, packed):
+            part = np.stack([orc.eval_dot_shard(k, prf, table, self.rank * (n // self.world), n // self.world)
+                             for k in packed.numpy()])
+            return self._reduce_to_rank0(torch.from_numpy(part))
+
+    d = OracleBackedShards(prf=prf)
     d.eval_init(torch.from_numpy(table))
     got_a = d.eval_gpu([torch.from_numpy(k) for k in ka])
     got_b = d.eval_gpu(torch.from_numpy(kb))
