@@ -70,6 +70,11 @@ def parse_args():
     ap.add_argument("--strong", action="store_true",
                     help="N>1: keep the GLOBAL batch at --batch-per-gpu keys (strong scaling: each GPU still sees "
                          "every key but only 1/N of the leaves) instead of growing it with N")
+    ap.add_argument("--axis", default="auto", choices=["auto", "entries", "keys"],
+                    help="N>1: entry-range shards + reduce, key-split replicas + gather, or auto (by n; --strong only: "
+                         "the default weak run is always entry-sharded, as BASELINE.json's metric names)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the bounded n x PRF sweep / strong-scaling / config extras")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-timing parity check of the timed batch")
     ap.add_argument("--reduce", default="nccl", choices=["nccl", "fused"],
                     help="N>1: NCCL reduce of the partials, or the kernel's peer-memory red.add epilogue")
     return ap.parse_args()
@@ -89,8 +94,49 @@ def synthetic_keys(n, batch, prf):
     import b200dpf
     rng = np.random.RandomState(4321)
     alphas = rng.randint(0, n, size=batch).astype(np.int64)
-    ka, _ = b200dpf.gen_batch(alphas, n, np.arange(batch) + 1000, prf)
-    return ka, alphas
+    ka, kb = b200dpf.gen_batch(alphas, n, np.arange(batch) + 1000, prf)
+    return ka, kb, alphas
+
+
+def host_cores():
+    """Host threads this process can really use: the scheduler affinity mask, capped by the
+    cgroup CPU quota when one is set (os.cpu_count() reports the machine, not the lease)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            f = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if f[0] != "max":
+                    cores = min(cores, max(1, int(int(f[0]) / int(f[1]))))
+            else:
+                quota = int(f[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    cores = min(cores, max(1, quota // period))
+            break
+        except Exception:
+            continue
+    return max(1, cores)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
 
 # ---------------------------------------------------------------------------
@@ -160,7 +206,7 @@ def cpu_reference_runner(n, entry, prf, table):
     sample and returns the number of DPF-equivalents it evaluated."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     orc = O.Oracle()
     rng = np.random.RandomState(99)
     keys = np.stack([orc.gen(int(rng.randint(0, n)), n, 2000 + i, prf)[0] for i in range(cores)])
@@ -212,7 +258,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": "n=%d entry_size=%d %s, reference CPU path (dpf_base EvaluateFlat per index) on host cores"
                                % (n, entry, args.prf.upper()), "n": n, "entry_size": entry, "prf": args.prf.upper()},
-        "cpu_baseline": {"value": value, "unit": "DPFs/sec", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "DPFs/sec", "cores": cores, "kind": kind, "sample": sample,
+                         "cpu_model": cpu_model()},
         "e2e": {"value": value, "unit": "DPFs/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -233,7 +280,7 @@ def run_reference_gpu(args):
     prf = PRF_IDS[args.prf]
     n, entry, batch = args.n, args.entry, args.batch_per_gpu
     table = synthetic_table(n, entry)
-    keys_np, _ = synthetic_keys(n, batch, prf)
+    keys_np, _, _ = synthetic_keys(n, batch, prf)
     keys = [torch.from_numpy(k) for k in keys_np]
     ref = refgpu.RefGpuDPF(prf)
     t0 = time.perf_counter()
@@ -262,152 +309,285 @@ def run_reference_gpu(args):
 # ---------------------------------------------------------------------------
 # our engine
 # ---------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def pipe_roofline(prf_name, dpfs_per_s, n_local, sm_mhz):
+    """Integer-pipe roofline from MEASURED peaks (profiles/int_peaks.json, written by
+    tools/microbench/int_pipes.cu on a B200) and MEASURED per-node-pair instruction counts
+    (profiles/pipe_ops.json, from ncu sm__inst_executed_pipe_* / l1tex wavefront counters of the
+    evaluation kernel).  One node pair = one parent expanded into two children for a warp of 32
+    keys; a DPF over n_local leaves has n_local - 1 of them."""
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "profiles", "int_peaks.json")))
+        ops = json.load(open(os.path.join(ROOT, "profiles", "pipe_ops.json")))[prf_name]
+    except Exception:
+        return None
+    pipe = ops["binding_pipe"]                      # "alu" | "lsu"
+    per_pair = float(ops["warp_inst_per_node_pair"][pipe])
+    peak_per_clk_sm = float(peaks["peak_warp_inst_per_clk_sm"][pipe])
+    sms = int(peaks.get("sms", 148))
+    mhz = float(sm_mhz or peaks.get("sm_max_mhz", 1965.0))
+    pairs_per_s = dpfs_per_s / 32.0 * max(n_local - 1, 1)
+    achieved = pairs_per_s * per_pair                # warp-instructions (or wavefronts) per second
+    peak = peak_per_clk_sm * sms * mhz * 1e6
+    return {"pipe": ops.get("pipe_name", pipe), "warp_inst_per_node_pair": per_pair,
+            "achieved_ginst_s": achieved / 1e9, "peak_ginst_s": peak / 1e9, "frac": achieved / peak,
+            "peak_source": "profiles/int_peaks.json (tools/microbench/int_pipes.cu, %s/clk/SM) x %d SMs x %.0f MHz"
+                           % (peak_per_clk_sm, sms, mhz),
+            "ops_source": ops.get("source", "profiles/pipe_ops.json")}
+
+
+class Harness:
+    """torch / process-group state shared by every measurement of one bench.py run."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU baseline)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            import datetime
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=600))
+        assert self.world == args.gpus or self.world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+        self.args = args
+
+    def barrier(self, world=None):
+        if (self.world if world is None else world) > 1:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x, world=None):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if (self.world if world is None else world) > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def parity_check(h, d, world, prf, table, keys_a, keys_b, alphas, n_oracle=4):
+    """Outside every timed region: the engine's results for the batch that was just timed,
+    checked (rank 0) by share reconstruction  a - b == table[alpha]  for EVERY key of the batch and
+    bit-exactly against the CPU oracle for the first n_oracle keys."""
+    torch = h.torch
+    ka = torch.from_numpy(keys_a).to(h.dev)
+    kb = torch.from_numpy(keys_b).to(h.dev)
+    ra = d.eval_gpu_device(ka)
+    a = ra.cpu().numpy().copy() if (world == 1 or h.rank == 0) else None
+    rb = d.eval_gpu_device(kb)
+    b = rb.cpu().numpy().copy() if (world == 1 or h.rank == 0) else None
+    if a is None:
+        return None
+    rec = (a.astype(np.uint32) - b.astype(np.uint32)).astype(np.int32)
+    bad = int((rec != table[alphas]).any(axis=1).sum())
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    orc = O.Oracle()
+    want = [None] * n_oracle
+
+    def one(i):
+        want[i] = orc.eval_dot(keys_a[i:i + 1], prf, table)[0]
+    th = [threading.Thread(target=one, args=(i,)) for i in range(n_oracle)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    bad_oracle = sum(0 if np.array_equal(a[i], want[i]) else 1 for i in range(n_oracle))
+    return {"keys_reconstructed": int(len(alphas)), "reconstruct_mismatches": bad, "keys_vs_oracle": n_oracle,
+            "oracle_mismatches": bad_oracle, "ok": bad == 0 and bad_oracle == 0,
+            "checksum": int(a.astype(np.int64).sum() & 0xFFFFFFFF)}
+
+
+def measure(h, prf_name, n, entry, batch, steps, warmup, world=None, axis="entries", reduce="nccl",
+            e2e=True, parity=4, settle_s=0.0, subtree_log2=0, sampler=None):
+    """One configuration: eval_init, warm-up, `steps` device-timed steps (CUDA events on the launching
+    stream, max over ranks, L2 flushed before every step), optionally the end-to-end leg through the
+    public host-buffer API, and the parity check of the timed batch.  world=1 on a multi-rank run
+    means: this rank alone, no collectives (other ranks must not call)."""
     import dpf as dpf_mod
     from sharded import ShardedDPF
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
-
-    prf = PRF_IDS[args.prf]
-    n, entry = args.n, args.entry
-    batch = args.batch_per_gpu * (1 if args.strong else world)
+    torch = h.torch
+    world = h.world if world is None else world
+    prf = PRF_IDS[prf_name]
     table = synthetic_table(n, entry)
-    keys_np, _ = synthetic_keys(n, batch, prf)
-
+    keys_a, keys_b, alphas = synthetic_keys(n, batch, prf)
     if world > 1:
-        d = ShardedDPF(prf=prf, device=local_rank, reduce=args.reduce)
+        d = ShardedDPF(prf=prf, device=h.local_rank, reduce=reduce, axis=axis)
         d.eval_init(torch.from_numpy(table))
         inner = d._dpf
+        axis_used = d.axis
     else:
-        d = dpf_mod.DPF(prf=prf, device=local_rank)
+        d = dpf_mod.DPF(prf=prf, device=h.local_rank)
         d.eval_init(torch.from_numpy(table))
         inner = d
-    if args.subtree_log2:
-        import dpf_cpp
-        dpf_cpp.set_subtree_log2(inner.buffers, args.subtree_log2)
-
-    keys_dev = torch.from_numpy(keys_np).to(dev)
-    out_dev = torch.empty((batch, entry), dtype=torch.int32, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+        axis_used = "single"
+    import dpf_cpp
+    if subtree_log2:
+        dpf_cpp.set_subtree_log2(inner.buffers, subtree_log2)
+    keys_dev = torch.from_numpy(keys_a).to(h.dev)
+    out_dev = torch.empty((batch, entry), dtype=torch.int32, device=h.dev)
 
     def step_device():
         d.eval_gpu_device(keys_dev, out_dev)
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()          # nvidia-smi needs a moment to produce its first sample
-    nwarm = max(args.warmup, 3)
+    nwarm = max(warmup, 3)
     t_warm = time.perf_counter()
     for _ in range(nwarm):
-        flush.zero_()
+        h.flush.zero_()
         step_device()
     torch.cuda.synchronize()
-    # keep the GPU busy for ~0.5 s in total so the clock sampler sees it under load; the number
-    # of extra iterations is decided on rank 0 and broadcast (collectives must match across ranks)
-    per_step = (time.perf_counter() - t_warm) / nwarm
-    extra = torch.tensor([int(min(2000, max(0, 0.5 / max(per_step, 1e-6) - nwarm)))], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(extra, src=0)
-    for i in range(int(extra.item())):
-        flush.zero_()
-        step_device()
-        if i % 16 == 15:
-            torch.cuda.synchronize()
-    nwarm += int(extra.item())
-    torch.cuda.synchronize()
-
-    import dpf_cpp
+    extra_n = 0
+    if settle_s > 0:
+        # keep the GPU busy for ~settle_s in total so the clock sampler sees it under load; the number
+        # of extra iterations is decided on rank 0 and broadcast (collectives must match across ranks)
+        per_step = (time.perf_counter() - t_warm) / nwarm
+        extra = torch.tensor([int(min(2000, max(0, settle_s / max(per_step, 1e-6) - nwarm)))], dtype=torch.int64, device=h.dev)
+        if world > 1:
+            h.dist.broadcast(extra, src=0)
+        extra_n = int(extra.item())
+        for i in range(extra_n):
+            h.flush.zero_()
+            step_device()
+            if i % 16 == 15:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
     launches_per_step = dpf_cpp.last_launches(inner.buffers)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    h.barrier(world)
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                       # cold L2 at the start of every timed step
+    for k in range(steps):
+        h.flush.zero_()                       # cold L2 at the start of every timed step
         starts[k].record()
         step_device()
         ends[k].record()
     torch.cuda.synchronize()
-    barrier()
+    h.barrier(world)
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    value = batch * args.steps / (dev_ms / 1e3)
+    dev_ms = h.max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends)), world)
+    res = {"value": batch * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps, "launches_per_step": launches_per_step,
+           "warmup_effective": nwarm + extra_n, "wall_s_timed_region": t_wall, "clocks": clocks, "axis": axis_used,
+           "batch": batch, "e2e": None, "parity_check": None}
 
-    # ---- end to end through the public API, host buffers ----
-    e2e = None
-    if not args.no_e2e:
-        keys_host = torch.from_numpy(keys_np).pin_memory()
+    if e2e:   # end to end through the public API: pinned HOST keys in, HOST result out, every step
+        keys_host = torch.from_numpy(keys_a).pin_memory()
         for _ in range(2):
             d.eval_gpu(keys_host)
-        barrier()
+        h.barrier(world)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = d.eval_gpu(keys_host)
+        for _ in range(steps):
+            r = d.eval_gpu(keys_host)
         torch.cuda.synchronize()
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        e2e = {"value": batch * args.steps / dt, "unit": "DPFs/sec",
-               "h2d_bytes_per_step": int(keys_host.numel() * 4) * world,
-               "d2h_bytes_per_step": int(batch * entry * 4)}
-        if rank == 0:
-            assert res is not None and tuple(res.shape) == (batch, entry)
+        h.barrier(world)
+        dt = h.max_over_ranks(time.perf_counter() - t0, world)
+        copies = world if axis_used == "entries" else 1       # entry shards: every rank uploads every key
+        res["e2e"] = {"value": batch * steps / dt, "unit": "DPFs/sec",
+                      "h2d_bytes_per_step": int(keys_host.numel() * 4) * copies,
+                      "d2h_bytes_per_step": int(batch * entry * 4)}
+        if h.rank == 0 or world == 1:
+            assert r is not None and tuple(r.shape) == (batch, entry)
+    if parity:
+        res["parity_check"] = parity_check(h, d, world, prf, table, keys_a, keys_b, alphas, n_oracle=parity)
+    d.close()
+    res["table"] = table
+    return res
+
+
+def run_ours(args):
+    h = Harness(args)
+    world, rank = h.world, h.rank
+    prf = PRF_IDS[args.prf]
+    n, entry = args.n, args.entry
+    batch = args.batch_per_gpu * (1 if args.strong else world)
+    sampler = ClockSampler(h.local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()          # nvidia-smi needs a moment to produce its first sample
+    axis = args.axis if (args.strong or args.axis != "auto") else "entries"
+    m = measure(h, args.prf, n, entry, batch, args.steps, args.warmup, axis=axis, reduce=args.reduce,
+                e2e=not args.no_e2e, parity=0 if args.no_parity else 4, settle_s=0.5,
+                subtree_log2=args.subtree_log2, sampler=sampler)
+    table = m.pop("table")
+    value, clocks = m["value"], m["clocks"]
+
+    # ---- bounded sweep over the other sizes / PRFs the north star names (N = 1), the BASELINE
+    # ---- configs that need 8 GPUs (N = 8), and strong scaling of ONE 512-key batch (N > 1)
+    sweep, strong, configs = [], None, []
+    if not args.no_sweep:
+        def entry_of(tag, prf_name, nn, ee, bb, r, ww=None):
+            ww = world if ww is None else ww
+            alg = bb * (nn * ee * 4 // (ww if r["axis"] == "entries" else 1) // 1 + KEY_BYTES + 4 * ee)
+            out = {"config": tag, "prf": prf_name.upper(), "n": nn, "entry_size": ee, "batch": bb, "n_gpus": ww,
+                   "axis": r["axis"], "value": r["value"], "ms_per_step": r["ms_per_step"],
+                   "e2e": r["e2e"]["value"] if r["e2e"] else None, "launches_per_step": r["launches_per_step"],
+                   "frac": (alg / (r["ms_per_step"] / 1e3) / 1e9) / (float(load_peaks().get("hbm_gbs", 6650.0)) * ww),
+                   "parity_ok": r["parity_check"]["ok"] if r["parity_check"] else None}
+            return out
+        try:
+            if world == 1:
+                for prf_name in ("aes128", "salsa20", "chacha20"):
+                    for nn in (1 << 14, 1 << 16, 1 << 18):
+                        r = measure(h, prf_name, nn, 16, 512, 10, 3, parity=2)
+                        r.pop("table")
+                        sweep.append(entry_of("n=2^%d" % (nn.bit_length() - 1), prf_name, nn, 16, 512, r))
+                r = measure(h, "aes128", 1 << 14, 16, 256, 20, 3, parity=2)      # BASELINE.json config 2
+                r.pop("table")
+                configs.append(entry_of("C2", "aes128", 1 << 14, 16, 256, r))
+            else:
+                strong = []
+                for nn in (1 << 16, 1 << 20):
+                    rs = measure(h, "aes128", nn, 16, 512, 10, 3, axis="auto", parity=2)
+                    rs.pop("table")
+                    one = None
+                    if rank == 0:          # the same batch on ONE of these GPUs, this rank alone
+                        one = measure(h, "aes128", nn, 16, 512, 10, 3, world=1, e2e=False, parity=0)
+                        one.pop("table")
+                    h.barrier()
+                    if rank == 0:
+                        strong.append({"n": nn, "prf": "AES128", "batch": 512, "axis": rs["axis"], "ms_per_step": rs["ms_per_step"],
+                                       "value": rs["value"], "ms_per_step_1gpu": one["ms_per_step"],
+                                       "speedup_vs_1gpu": one["ms_per_step"] / rs["ms_per_step"],
+                                       "parity_ok": rs["parity_check"]["ok"] if rs["parity_check"] else None})
+                if world == 8 and not args.strong:
+                    r = measure(h, "salsa20", 1 << 24, 16, 4096, 2, 3, e2e=False, parity=2)      # config 4
+                    r.pop("table")
+                    configs.append(entry_of("C4", "salsa20", 1 << 24, 16, 4096, r))
+                    r = measure(h, "aes128", 1 << 20, 128, 8192, 2, 3, e2e=False, parity=2)      # config 5
+                    r.pop("table")
+                    configs.append(entry_of("C5", "aes128", 1 << 20, 128, 8192, r))
+        except Exception as exc:   # the headline line must survive a failure in the extras
+            sweep.append({"error": "%s: %s" % (type(exc).__name__, exc)})
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         # dominant kernel = the one evaluation kernel of a step; per launch it processes `batch`
         # keys over n/world leaves each
-        alg_bytes = batch * (n // world * entry * 4 + KEY_BYTES + 4 * entry)
-        launch_ms = dev_ms / args.steps
+        shards = world if m["axis"] == "entries" else 1
+        alg_bytes = batch * (n // shards * entry * 4 + KEY_BYTES + 4 * entry)
+        launch_ms = m["ms_per_step"]
         achieved = alg_bytes / (launch_ms / 1e3) / 1e9
         traffic = None
-        try:   # measured once per change with `ncu --set full` (tools/gpu_round1_final.sh), per launch
+        try:   # measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum), per launch: tools/gpu_r2_traffic.sh
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             key = "%s_n%d_e%d_b%d_%dgpu" % (args.prf, n, entry, batch, world)
             traffic = tr.get(key, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
-        binding = {"aes128": {"pipe": "l1tex data pipe (shared-memory T-table wavefronts)", "busy_frac": 0.979},
-                   "salsa20": {"pipe": "integer ALU pipe (LOP3/SHF)", "busy_frac": 0.977},
-                   "chacha20": {"pipe": "integer ALU pipe (LOP3/SHF)", "busy_frac": 0.954}}.get(args.prf)
-        roofline = {"bound": "hbm", "binding_pipe_ncu": binding, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_kind,
+                    "pipe": pipe_roofline(args.prf, value / world, n // shards, (clocks or {}).get("sm_mhz")),
                     "note": "algorithmic bytes = batch*(n*E*4/ngpu + 2096 + 4E) per launch (table streamed once "
                             "per key, SURVEY 8d); actual DRAM traffic is far lower because 32 keys share each row "
-                            "load and the table stays in L2. The binding resource is the LSU/shared-memory data "
-                            "pipe for AES (97.9% busy, ncu) and the ALU pipe for Salsa/ChaCha (97.7%): DESIGN.md s4"}
+                            "load and the table stays in L2, so the HBM fraction is nominal.  `pipe` is the roofline "
+                            "that binds: measured instruction count per node pair / measured pipe issue rate."}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             kind, cores, sample, step = cpu_reference_runner(n, entry, prf, table)
@@ -415,29 +595,42 @@ def run_ours(args):
             t0 = time.perf_counter()
             units = step()
             cpu = {"value": units / (time.perf_counter() - t0), "unit": "DPFs/sec", "cores": cores, "kind": kind,
-                   "sample": sample}
+                   "sample": sample, "cpu_model": cpu_model()}
         published = BASELINE_PUBLISHED.get((args.prf, n)) if (entry == 16) else None
+        par = m["parity_check"]
         line = {
             "metric": "DPFs/sec", "value": value, "unit": "DPFs/sec", "n_gpus": world, "steps": args.steps,
-            "warmup": nwarm, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "warmup_effective": m["warmup_effective"],
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if args.strong else "weak",
             "vs_baseline": (value / published) if published else None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": "n=%d entry_size=%d %s batch=%d (%s), table entry-range sharded over %d GPU(s)"
+            "config": {"workload": "n=%d entry_size=%d %s batch=%d (%s), %s over %d GPU(s)"
                                    % (n, entry, args.prf.upper(), batch,
-                                      "fixed global batch" if args.strong else "%d per GPU" % args.batch_per_gpu, world),
+                                      "fixed global batch" if args.strong else "%d per GPU" % args.batch_per_gpu,
+                                      "batch split by keys, table replicated" if m["axis"] == "keys" else "table entry-range sharded",
+                                      world),
                        "n": n, "entry_size": entry, "prf": args.prf.upper(), "global_batch": batch,
-                       "parallelism": ("entry-shard x%d + %s" % (world, "NCCL reduce" if args.reduce == "nccl" else
-                                       "in-kernel peer-memory red.add (symmetric memory)")) if world > 1 else "single GPU",
-                       "l2": "256 MiB device buffer zeroed before every timed step (L2 flush); table 64 MiB",
+                       "parallelism": ("%s x%d + %s" % ("entry-shard" if m["axis"] == "entries" else "key-split", world,
+                                       ("NCCL reduce" if args.reduce == "nccl" else "in-kernel peer-memory red.add (symmetric memory)")
+                                       if m["axis"] == "entries" else "NCCL gather")) if world > 1 else "single GPU",
+                       "l2": "256 MiB device buffer zeroed before every timed step (L2 flush); table %d MiB" % (n * entry * 4 >> 20),
                        "vs_baseline_ref": "reference README V100 number (BASELINE.md)" if published else None},
-            "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
-            "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": t_wall,
+            "e2e": m["e2e"], "gpu_launches": m["launches_per_step"] * args.steps, "roofline": roofline,
+            "cpu_baseline": cpu, "clocks": clocks, "wall_s_timed_region": m["wall_s_timed_region"],
+            "parity_check": par,
         }
+        if sweep:
+            line["sweep"] = sweep
+        if configs:
+            line["configs"] = configs
+        if strong:
+            line["strong"] = strong
         emit(line)
-    d.close()
-    if world > 1:
-        dist.destroy_process_group()
+        if par is not None and not par["ok"]:
+            h.close()
+            raise SystemExit("bench.py: PARITY FAILURE in the timed batch: %r" % (par,))
+    h.close()
 
 
 def main():

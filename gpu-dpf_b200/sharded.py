@@ -57,13 +57,19 @@ def key_slice(nkeys, rank, world):
 class ShardedDPF(object):
     """dpf.DPF semantics over a process group; rank 0 receives the result."""
 
+    # axis="auto": below this table size a shard is too small to keep a GPU busy and the partial-sum
+    # reduce + the upload of every key to every rank dominate; the batch is split by keys instead
+    AUTO_KEYS_MAX_N = 1 << 18
+
     def __init__(self, prf=None, group=None, device=None, axis="entries", reduce="nccl"):
-        assert axis in ("entries", "keys") and reduce in ("nccl", "fused")
+        assert axis in ("entries", "keys", "auto") and reduce in ("nccl", "fused")
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         if axis == "entries" and self.world & (self.world - 1):
             raise Exception("number of shards (%d) must be a power of two" % self.world)
+        if axis == "auto" and self.world & (self.world - 1):
+            axis = "keys"
         self.device = int(os.environ.get("LOCAL_RANK", self.rank)) if device is None else device
         self.axis = axis
         self.reduce = reduce if self.world > 1 else "nccl"
@@ -76,6 +82,8 @@ class ShardedDPF(object):
     def eval_init(self, table):
         self.n, self.entry_size = table.shape[0], table.shape[1]
         import dpf
+        if self.axis == "auto":
+            self.axis = "keys" if (self.n <= self.AUTO_KEYS_MAX_N or self.world > self.n // 2) else "entries"
         shard = (self.rank, self.world) if self.axis == "entries" else (0, 1)
         self._dpf = dpf.DPF(prf=self.prf, device=self.device, shard=shard)
         self._dpf.eval_init(table)
@@ -120,7 +128,14 @@ class ShardedDPF(object):
             hdl.barrier(channel=0)                 # destination cleared before anyone adds
             self._dpf.eval_gpu_device(keys_dev, out_ptr=root_ptr, accumulate=True)
             hdl.barrier(channel=1)                 # every rank's adds have landed
-            return view
+            if self.rank != 0:
+                return None
+            # the symmetric buffer is reused (and re-zeroed) by the next call: hand the caller a tensor
+            # it owns, like the NCCL path does
+            if out_dev is None:
+                return view.clone()
+            out_dev.copy_(view)
+            return out_dev
         out_dev = self._dpf.eval_gpu_device(keys_dev, out_dev)
         return self._reduce_to_rank0(out_dev)
 
@@ -130,8 +145,21 @@ class ShardedDPF(object):
             packed = keys.contiguous()
         else:
             packed = torch.stack(list(keys))
+        self._check_keys(packed)
         out = self._evaluate_and_combine(packed)
         return out.cpu() if self.rank == 0 else None
+
+    def _check_keys(self, packed):
+        """The device-resident path takes the tree depth from the context, not from the key: refuse
+        keys made for another domain size here, as DPF.eval_gpu does (slot 130 = n, slot 0 = depth)."""
+        if packed.dtype != torch.int32 or packed.dim() != 2 or packed.shape[1] != 524:
+            raise Exception("keys must be int32 [B, 524]")
+        if self.n is None or packed.shape[0] == 0:
+            return
+        n_lo, depth = packed[:, 130 * 4], packed[:, 0]
+        n_word = self.n if self.n < 2 ** 31 else self.n - 2 ** 32
+        if not bool(((n_lo == n_word) & (depth == self.n.bit_length() - 1)).all()):
+            raise RuntimeError("a key was generated for a different table size than n=%d" % self.n)
 
     def _evaluate_and_combine(self, packed):
         """This rank's evaluation on its GPU plus the cross-rank step; the tensor returned on

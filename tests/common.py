@@ -42,3 +42,19 @@ def dot_u32(shares, table):
         prod = (s * t[:, e][None, :]) & np.uint64(0xFFFFFFFF)
         out[:, e] = prod.sum(axis=1) & np.uint64(0xFFFFFFFF)
     return out.astype(np.uint32).astype(np.int32)
+
+
+def oracle_dot_mt(oracle, keys, prf, table, nthreads=16):
+    """oracle.eval_dot over several host threads (ctypes releases the GIL): the tree-expansion
+    oracle costs seconds per key at n >= 2^20, and the GPU box has cores to spare."""
+    import threading
+    keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 524)
+    out = [None] * keys.shape[0]
+
+    def work(t):
+        for i in range(t, keys.shape[0], nthreads):
+            out[i] = oracle.eval_dot(keys[i:i + 1], prf, table)[0]
+    th = [threading.Thread(target=work, args=(t,)) for t in range(min(nthreads, keys.shape[0]))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    return np.stack(out)
