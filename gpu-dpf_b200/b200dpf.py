@@ -20,6 +20,7 @@ PRF_NAMES = {0: "DUMMY", 1: "SALSA20", 2: "CHACHA20", 3: "AES128"}
 SYMBOLS = [
     "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_eval_cpu",
     "b200dpf_key_packed_size", "b200dpf_key_pack", "b200dpf_key_unpack", "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
+    "b200dpf_eval_packed", "b200dpf_ctx_set_option",
     "b200dpf_host_staging", "b200dpf_eval_device", "b200dpf_eval_device_acc", "b200dpf_expand_device", "b200dpf_ctx_n", "b200dpf_ctx_entry_size",
     "b200dpf_ctx_device", "b200dpf_ctx_last_launches", "b200dpf_ctx_set_subtree_log2",
 ]
@@ -53,6 +54,8 @@ def load():
     L.b200dpf_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
     L.b200dpf_destroy.argtypes = [C.c_void_p]
     L.b200dpf_eval.argtypes = [C.c_void_p, _i32p, C.c_int64, C.c_int, _i32p]
+    L.b200dpf_eval_packed.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int, _i32p]
+    L.b200dpf_ctx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.b200dpf_host_staging.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.POINTER(C.c_int32))]
     L.b200dpf_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     L.b200dpf_eval_device_acc.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
@@ -154,6 +157,15 @@ class Context:
         out = np.zeros((keys.shape[0], self.entry_size), np.int32)
         _check(lib().b200dpf_eval(self.handle, keys, keys.shape[0], prf, out), "b200dpf_eval")
         return out
+
+    def eval_packed(self, packed, nkeys, prf):
+        """keys in the compact wire form (key_pack), concatenated"""
+        out = np.zeros((nkeys, self.entry_size), np.int32)
+        _check(lib().b200dpf_eval_packed(self.handle, bytes(packed), nkeys, prf, out), "b200dpf_eval_packed")
+        return out
+
+    def set_option(self, name, value):
+        _check(lib().b200dpf_ctx_set_option(self.handle, name.encode(), int(value)), "b200dpf_ctx_set_option")
 
     def eval_device(self, keys_ptr, nkeys, prf, out_ptr, stream=0, accumulate=False):
         fn = lib().b200dpf_eval_device_acc if accumulate else lib().b200dpf_eval_device

@@ -98,8 +98,30 @@ struct b200dpf_ctx {
     size_t h_out_cap = 0;       /* int32 elements */
     int sm_count = 0;
     uint32_t smem_base = 0;
-    int s_override = 0;
     int last_launches = 0;
+    /* tuning knobs: defaults from the environment, read ONCE at b200dpf_create; changed per
+     * context with b200dpf_ctx_set_option */
+    struct Knobs {
+        int leaf_cache = 1;        /* B200DPF_LEAF_CACHE     wide entries: cache leaves, MAC-only passes  */
+        int leaf_cache_mb = 16384; /* B200DPF_LEAF_CACHE_MB  cap; larger batches are evaluated in chunks   */
+        int lane_split = 1;        /* B200DPF_LANE_SPLIT     batches < 32 keys: lane = (key, subtree)      */
+        int frontier = 1;          /* B200DPF_FRONTIER       expand the tree top once per evaluation       */
+        int frontier_mb = 256;     /* B200DPF_FRONTIER_MB                                                  */
+        int subtree_log2 = 0;      /* B200DPF_S              0 = automatic                                  */
+        int mac_tma = 1;           /* B200DPF_MAC_TMA        cp.async.bulk-staged MAC passes               */
+        int one_launch = 1;        /* B200DPF_ONE_LAUNCH     whole evaluation as one cooperative launch    */
+    } knobs;
+    int coop_ok = 0;               /* device supports cooperative launches                                 */
+    uint32_t *d_top_counters = nullptr;   /* top-phase tickets: zero between launches (self re-arming)     */
+    size_t top_counters_cap = 0;          /* bytes                                                          */
+    uint32_t *d_gridbar = nullptr;        /* monotonic arrival counter of the in-kernel grid barrier        */
+    uint32_t bar_epoch = 0;               /* value d_gridbar holds when no launch is in flight              */
+    bool coop_state_dirty = true;         /* top tickets / barrier counter must be cleared before use       */
+    /* one evaluation in flight per context: launches on a different stream than the previous
+     * evaluation first wait for it (the scratch buffers above are shared)                                 */
+    cudaEvent_t ev_done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_last = false;
 };
 
 namespace {
@@ -190,12 +212,12 @@ int smem_layout_compute(b200dpf_ctx *c, int prf, int nv, int mode, SmemLayout *L
     return B200DPF_OK;
 }
 
+/* s = the deepest pending-sibling stack any phase of the launch needs */
 void fill_common(const b200dpf_ctx *c, const SmemLayout &L, int s, int64_t nkeys, int kpw_log2, EvalParams *p,
                  size_t *smem)
 {
     std::memset(p, 0, sizeof *p);
     p->depth = c->depth;
-    p->s = s;
     p->nkeys = (int)nkeys;
     p->kpw_log2 = kpw_log2;
     p->key_groups = (int)((nkeys + (1 << kpw_log2) - 1) >> kpw_log2);
@@ -209,7 +231,6 @@ void fill_common(const b200dpf_ctx *c, const SmemLayout &L, int s, int64_t nkeys
     p->off_flag = p->off_root + 512u;
     p->off_stack_lo = L.off_lo;
     p->off_stack_hi = L.off_hi;
-    p->stack_split = std::min(L.cap_lo, s - 1);
     p->off_tab = L.off_tab;
     *smem = L.smem_fixed ? L.smem_fixed : (size_t)L.off_lo + (size_t)(s > 1 ? s - 1 : 0) * L.level_bytes;
 }
@@ -231,23 +252,36 @@ int ensure_buffer(void **ptr, size_t *cap, size_t bytes)
     return B200DPF_OK;
 }
 
+/* Where the kernel finds the live parts of a key. */
+struct KeyLayout {
+    uint32_t stride_v, root_v;
+    int compact;
+};
+KeyLayout reference_layout() { return KeyLayout{131u, 129u, 0}; }                       /* dpf_wrapper.cu:26-46 */
+KeyLayout compact_layout(int depth) { return KeyLayout{2u + 4u * (uint32_t)depth, 1u, 1}; }   /* b200dpf_key_pack */
+
+void fill_phase(const SmemLayout &L, int s, PhaseParams *ph)
+{
+    std::memset(ph, 0, sizeof *ph);
+    ph->s = s;
+    ph->stack_split = std::min(L.cap_lo, std::max(s - 1, 0));
+}
+
 /*
- * The launch pipeline of one evaluation:
- *   [memset tickets (+ out)]  ->  [frontier kernel]  ->  main kernel x passes
+ * One evaluation of <= one leaf-cache-full of keys:
+ *   one launch  : [clear result + tickets, build frontier | grid barrier | main]  (+ MAC passes)
+ *   legacy      : memset tickets, memset result, frontier kernel, main kernel x passes
  * mode_main is MODE_FUSED (out = [nkeys][entry_size] int32) or MODE_EXPAND
  * (out = [nkeys][n] int32 share vectors).
  */
-int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, int mode_main, void *out_dev,
-                 cudaStream_t stream, bool clear_out = true)
+int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl, int64_t nkeys, int prf, int mode_main,
+                       void *out_dev, cudaStream_t stream, bool clear_out, bool want_cache)
 {
+    const b200dpf_ctx::Knobs &K = c->knobs;
     /* Entries wider than 32 columns: the tree is expanded ONCE by the best-shaped kernel (16
      * columns, NV = 4), which also caches each leaf's low word; every other column is produced by
-     * MAC-only passes over that cache.  Without the cache (disabled, lane-split batches, or a cache
-     * larger than the cap) wide entries fall back to one tree expansion per 64 columns. */
-    const size_t cache_bytes_est = (size_t)((nkeys + 31) / 32) * 32u * (size_t)c->n_local * sizeof(uint32_t);
-    const bool want_cache = mode_main == MODE_FUSED && c->entry_pad > 32 && nkeys >= 17 &&
-                            env_int("B200DPF_LEAF_CACHE", 1) != 0 &&
-                            cache_bytes_est <= ((size_t)env_int("B200DPF_LEAF_CACHE_MB", 16384) << 20);
+     * MAC-only passes over that cache.  Without the cache (disabled or lane-split batches) wide
+     * entries use one tree expansion per 64 columns. */
     const int nv = (mode_main != MODE_FUSED || c->entry_pad <= 16 || want_cache) ? 4 : (c->entry_pad <= 32 ? 8 : 16);
     const int passes = mode_main == MODE_FUSED ? (want_cache ? 1 : c->entry_pad / (4 * nv)) : 1;
     SmemLayout L;
@@ -257,7 +291,7 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
     /* keys per warp: a full warp of keys when the batch allows; for small batches the
      * spare lanes take adjacent subtrees of the same keys (single-query latency mode) */
     int kpw_log2 = 5;
-    if (env_int("B200DPF_LANE_SPLIT", 1) != 0)
+    if (K.lane_split != 0)
         while (kpw_log2 > 0 && ((int64_t)1 << (kpw_log2 - 1)) >= nkeys) kpw_log2--;
     int64_t key_groups = (nkeys + ((int64_t)1 << kpw_log2) - 1) >> kpw_log2;
 
@@ -265,11 +299,10 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
      * measured on B200 (profiles/r1_sweeps.txt).  Without a frontier every item
      * re-walks depth-s levels from the root, so items must be big; with one the
      * walk is (almost) free and small items balance the tail. */
-    const bool want_frontier = env_int("B200DPF_FRONTIER", 1) != 0;
-    const int s_env = c->s_override > 0 ? c->s_override : env_int("B200DPF_S", 0);
+    const bool want_frontier = K.frontier != 0;
     int s;
-    if (s_env > 0) {
-        s = std::min(s_env, std::min(c->depth_local, L.s_max));
+    if (K.subtree_log2 > 0) {
+        s = std::min(K.subtree_log2, std::min(c->depth_local, L.s_max));
     } else {
         /* B=512 E=16 1xB200, DPFs/s (profiles/r1_sweeps.txt):
          *   AES n=2^20, frontier: s=4 23.99k, 5 24.83k, 6 25.03k, 7 25.01k, 8 24.92k; no frontier s=8 24.19k
@@ -291,71 +324,133 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         key_groups = (nkeys + ((int64_t)1 << kpw_log2) - 1) >> kpw_log2;
     }
     const int spw_log2 = 5 - kpw_log2;
+    if (want_cache && kpw_log2 != 5) return fail(B200DPF_ESTATE, "internal: leaf cache planned for a lane-split batch");
 
     int f_rel = 0;                                /* frontier depth below the shard root (0 = none) */
     if (want_frontier && rel >= 2) {
-        const int64_t cap_bytes = (int64_t)env_int("B200DPF_FRONTIER_MB", 256) << 20;
+        const int64_t cap_bytes = (int64_t)K.frontier_mb << 20;
         f_rel = rel;
         while (f_rel > 0 && ((key_groups * (16 << kpw_log2)) << f_rel) > cap_bytes) f_rel--;
         if (f_rel < 2 || f_rel < spw_log2 + 1) f_rel = 0;
     }
 
-    const size_t n_counters = (size_t)(passes + 1) * (size_t)key_groups;
-    rc = ensure_buffer(reinterpret_cast<void **>(&c->d_counters), &c->counters_cap, n_counters * sizeof(uint32_t));
+    const bool one_launch = K.one_launch != 0 && c->coop_ok != 0;
+    const size_t n_main_counters = (size_t)passes * (size_t)key_groups;
+    rc = ensure_buffer(reinterpret_cast<void **>(&c->d_counters), &c->counters_cap, n_main_counters * sizeof(uint32_t));
     if (rc) return rc;
-    CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, n_counters * sizeof(uint32_t), stream));
-    if (mode_main == MODE_FUSED && clear_out)
-        CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)nkeys * c->entry_size * sizeof(int32_t), stream));
-    c->last_launches = 0;
-
-    EvalParams p;
-    size_t smem;
+    {
+        const size_t before = c->top_counters_cap;
+        rc = ensure_buffer(reinterpret_cast<void **>(&c->d_top_counters), &c->top_counters_cap,
+                           std::max<size_t>((size_t)key_groups, 64) * sizeof(uint32_t));
+        if (rc) return rc;
+        if (c->top_counters_cap != before) c->coop_state_dirty = true;
+    }
     if (f_rel > 0) {
         rc = ensure_buffer(reinterpret_cast<void **>(&c->d_frontier), &c->frontier_cap,
                            ((size_t)key_groups * (16 << kpw_log2)) << f_rel);
         if (rc) return rc;
-        SmemLayout LF;
-        rc = smem_layout(c, prf, 4, MODE_FRONTIER, &LF);
-        if (rc) return rc;
-        const int s_top = std::max(1, std::min(f_rel - spw_log2, std::min(5, LF.s_max)));
-        fill_common(c, LF, s_top, nkeys, kpw_log2, &p, &smem);
-        p.keys = reinterpret_cast<const uint4 *>(keys_dev);
-        p.nsub = (uint32_t)1 << (f_rel - s_top);
-        p.sub_first = (uint32_t)c->shard_rank << (f_rel - s_top);
-        p.walk_first_level = c->depth - 1;
-        p.walk_steps = c->shard_bits + f_rel - s_top;
-        p.level_base = c->depth_local - f_rel;
-        p.nfront = (uint32_t)1 << f_rel;
-        p.frontier_out = reinterpret_cast<uint4 *>(c->d_frontier);
-        p.counters = c->d_counters + (size_t)passes * key_groups;
-        CUDA_TRY(launch_eval(prf, 4, MODE_FRONTIER, p, LF.grid, smem, stream));
-        c->last_launches++;
     }
 
-    fill_common(c, L, s, nkeys, kpw_log2, &p, &smem);
-    p.keys = reinterpret_cast<const uint4 *>(keys_dev);
-    p.nsub = (uint32_t)1 << rel;
-    p.sub_first = (uint32_t)c->shard_rank << rel;
-    if (f_rel > 0) {
-        p.frontier_in = reinterpret_cast<const uint4 *>(c->d_frontier);
-        p.nfront = (uint32_t)1 << f_rel;
-        p.front_shift = rel - f_rel;
-        p.walk_first_level = c->depth_local - f_rel - 1;
-        p.walk_steps = rel - f_rel;
-    } else {
-        p.walk_first_level = c->depth - 1;
-        p.walk_steps = c->depth - s;
+    /* one evaluation in flight per context (shared scratch): order after the previous one */
+    if (c->has_last && c->last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, c->ev_done, 0));
+
+    if (!one_launch || c->coop_state_dirty) {
+        CUDA_TRY(cudaMemsetAsync(c->d_top_counters, 0, c->top_counters_cap, stream));
+        CUDA_TRY(cudaMemsetAsync(c->d_gridbar, 0, sizeof(uint32_t), stream));
+        c->bar_epoch = 0;
+        c->coop_state_dirty = false;
     }
+    if (!one_launch) {
+        CUDA_TRY(cudaMemsetAsync(c->d_counters, 0, n_main_counters * sizeof(uint32_t), stream));
+        if (mode_main == MODE_FUSED && clear_out)
+            CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)nkeys * c->entry_size * sizeof(int32_t), stream));
+        c->coop_state_dirty = true;     /* the stand-alone frontier kernel leaves its tickets used */
+    }
+    c->last_launches = 0;
+
+    /* ---- the tree-top phase (frontier build) ---- */
+    EvalParams p;
+    size_t smem;
+    PhaseParams top;
+    std::memset(&top, 0, sizeof top);
+    int s_top = 0;
+    if (f_rel > 0) {
+        SmemLayout LF = L;
+        if (!one_launch) {
+            rc = smem_layout(c, prf, 4, MODE_FRONTIER, &LF);
+            if (rc) return rc;
+        }
+        s_top = std::max(1, std::min(f_rel - spw_log2, std::min(5, LF.s_max)));
+        fill_phase(LF, s_top, &top);
+        top.nsub = (uint32_t)1 << (f_rel - s_top);
+        top.sub_first = (uint32_t)c->shard_rank << (f_rel - s_top);
+        top.walk_first_level = c->depth - 1;
+        top.walk_steps = c->shard_bits + f_rel - s_top;
+        top.level_base = c->depth_local - f_rel;
+        top.counters = c->d_top_counters;
+        if (!one_launch) {
+            fill_common(c, LF, s_top, nkeys, kpw_log2, &p, &smem);
+            p.keys = reinterpret_cast<const uint4 *>(keys_dev);
+            p.key_stride_v = kl.stride_v; p.key_root_v = kl.root_v; p.key_compact = kl.compact;
+            p.main = top;
+            p.nfront = (uint32_t)1 << f_rel;
+            p.frontier_out = reinterpret_cast<uint4 *>(c->d_frontier);
+            CUDA_TRY(launch_eval(prf, 4, MODE_FRONTIER, p, LF.grid, smem, stream));
+            c->last_launches++;
+        }
+    }
+
+    /* ---- the main phase ---- */
+    fill_common(c, L, std::max(s, s_top), nkeys, kpw_log2, &p, &smem);
+    p.keys = reinterpret_cast<const uint4 *>(keys_dev);
+    p.key_stride_v = kl.stride_v; p.key_root_v = kl.root_v; p.key_compact = kl.compact;
+    fill_phase(L, s, &p.main);
+    p.main.nsub = (uint32_t)1 << rel;
+    p.main.sub_first = (uint32_t)c->shard_rank << rel;
+    if (f_rel > 0) {
+        p.main.frontier_in = reinterpret_cast<const uint4 *>(c->d_frontier);
+        p.nfront = (uint32_t)1 << f_rel;
+        p.main.front_shift = rel - f_rel;
+        p.main.walk_first_level = c->depth_local - f_rel - 1;
+        p.main.walk_steps = rel - f_rel;
+    } else {
+        p.main.walk_first_level = c->depth - 1;
+        p.main.walk_steps = c->depth - s;
+    }
+    p.main.counters = c->d_counters;
+    if (one_launch) {
+        p.fuse_top = 1;
+        p.top = top;                      /* nsub == 0: no frontier, the top phase only clears */
+        p.frontier_out = reinterpret_cast<uint4 *>(c->d_frontier);
+        if (mode_main == MODE_FUSED && clear_out) {
+            p.zero_a = reinterpret_cast<uint32_t *>(out_dev);
+            p.zero_a_words = (uint64_t)nkeys * (uint64_t)c->entry_size;
+        }
+        p.zero_b = c->d_counters;
+        p.zero_b_words = n_main_counters;
+        p.rearm = c->d_top_counters;
+        p.rearm_words = (uint32_t)key_groups;
+        p.grid_bar = c->d_gridbar;
+        c->bar_epoch += (uint32_t)L.grid;
+        p.grid_bar_target = c->bar_epoch;
+    }
+    auto launch_main = [&](int nv_l, int mode_l) -> int {
+        const cudaError_t e = launch_eval(prf, nv_l, mode_l, p, L.grid, smem, stream);
+        if (e != cudaSuccess) {
+            c->coop_state_dirty = true;
+            return fail(B200DPF_ECUDA, "evaluation kernel launch: %s", cudaGetErrorString(e));
+        }
+        c->last_launches++;
+        p.fuse_top = 0;                   /* later passes of this evaluation reuse the frontier */
+        return B200DPF_OK;
+    };
     if (mode_main == MODE_EXPAND) {
         p.shares = reinterpret_cast<uint32_t *>(out_dev);
-        p.counters = c->d_counters;
-        CUDA_TRY(launch_eval(prf, 4, MODE_EXPAND, p, L.grid, smem, stream));
-        c->last_launches++;
-        return B200DPF_OK;
+        return launch_main(4, MODE_EXPAND);
     }
     p.out = reinterpret_cast<uint32_t *>(out_dev);
-    const size_t cache_bytes = (size_t)key_groups * 32u * (size_t)c->n_local * sizeof(uint32_t);
-    if (want_cache && kpw_log2 == 5) {
+    if (want_cache) {
+        const size_t cache_bytes = (size_t)key_groups * 32u * (size_t)c->n_local * sizeof(uint32_t);
         rc = ensure_buffer(&c->d_leaf_cache, &c->leaf_cache_cap, cache_bytes);
         if (rc) return rc;
         p.leaf_cache = reinterpret_cast<uint32_t *>(c->d_leaf_cache);
@@ -363,9 +458,8 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         p.col_off_v = 0;
         p.col_off = 0;
         p.ncols = (uint32_t)std::min(16, c->entry_size);
-        p.counters = c->d_counters;
-        CUDA_TRY(launch_eval(prf, 4, MODE_FUSED, p, L.grid, smem, stream));
-        c->last_launches++;
+        rc = launch_main(4, MODE_FUSED);
+        if (rc) return rc;
         MacParams m;
         std::memset(&m, 0, sizeof m);
         m.leaf_cache = p.leaf_cache;
@@ -376,7 +470,7 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         m.nkeys = (int)nkeys;
         m.key_groups = (int)key_groups;
         m.n_local = (uint64_t)c->n_local;
-        const bool use_tma = env_int("B200DPF_MAC_TMA", 1) != 0;
+        const bool use_tma = K.mac_tma != 0;
         const int mac_grid = c->sm_count * 2;                      /* register-staged variant */
         const int64_t mac_warps = (int64_t)mac_grid * 8;
         int64_t ranges = std::max<int64_t>(1, (2 * mac_warps + key_groups - 1) / key_groups);
@@ -402,22 +496,60 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, i
         }
         return B200DPF_OK;
     }
-    if (want_cache) return fail(B200DPF_ESTATE, "internal: leaf cache planned for a lane-split batch");
     for (int pass = 0; pass < passes; pass++) {
         p.col_off_v = (uint32_t)(pass * nv);
         p.col_off = (uint32_t)(pass * 4 * nv);
         p.ncols = (uint32_t)std::max(0, std::min(4 * nv, c->entry_size - pass * 4 * nv));
         if (p.ncols == 0) break;
-        p.counters = c->d_counters + (size_t)pass * key_groups;
-        CUDA_TRY(launch_eval(prf, nv, MODE_FUSED, p, L.grid, smem, stream));
-        c->last_launches++;
+        p.main.counters = c->d_counters + (size_t)pass * key_groups;
+        rc = launch_main(nv, MODE_FUSED);
+        if (rc) return rc;
     }
     return B200DPF_OK;
 }
 
+/*
+ * One evaluation.  Wide entries whose leaf cache (nkeys x n_local x 4 bytes) would exceed the cap
+ * are evaluated in batch chunks that fit -- the cache is what makes columns beyond the first 16
+ * cost a MAC pass instead of a tree expansion, so shrinking the chunk beats dropping the cache.
+ */
+int run_pipeline(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl, int64_t nkeys, int prf, int mode_main,
+                 void *out_dev, cudaStream_t stream, bool clear_out = true)
+{
+    const b200dpf_ctx::Knobs &K = c->knobs;
+    int rc = B200DPF_OK;
+    int launches = 0;
+    const bool wide = mode_main == MODE_FUSED && c->entry_pad > 32 && nkeys >= 17 && K.leaf_cache != 0;
+    const size_t per_group = 32u * (size_t)c->n_local * sizeof(uint32_t);
+    const size_t cap = (size_t)std::max(K.leaf_cache_mb, 1) << 20;
+    if (!wide || per_group > cap) {
+        /* not a cached evaluation (or one key group alone overflows the cap: re-expand per 64 columns) */
+        rc = run_pipeline_chunk(c, keys_dev, kl, nkeys, prf, mode_main, out_dev, stream, clear_out, false);
+        launches = c->last_launches;
+    } else {
+        const int64_t groups_per_chunk = (int64_t)std::max<size_t>(1, cap / per_group);
+        const int64_t chunk = groups_per_chunk * 32;
+        for (int64_t k0 = 0; k0 < nkeys && rc == B200DPF_OK; k0 += chunk) {
+            const int64_t kn = std::min(chunk, nkeys - k0);
+            const char *kp = reinterpret_cast<const char *>(keys_dev) + (size_t)k0 * kl.stride_v * 16u;
+            char *op = reinterpret_cast<char *>(out_dev) + (size_t)k0 * c->entry_size * sizeof(int32_t);
+            /* a ragged tail below 17 keys would be lane-split, which the cache layout excludes */
+            rc = run_pipeline_chunk(c, kp, kl, kn, prf, mode_main, op, stream, clear_out, kn >= 17);
+            launches += c->last_launches;
+        }
+    }
+    c->last_launches = launches;
+    if (rc == B200DPF_OK) {
+        CUDA_TRY(cudaEventRecord(c->ev_done, stream));
+        c->last_stream = stream;
+        c->has_last = true;
+    }
+    return rc;
+}
+
 int run_eval(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *out_dev, cudaStream_t stream)
 {
-    return run_pipeline(c, keys_dev, nkeys, prf, MODE_FUSED, out_dev, stream);
+    return run_pipeline(c, keys_dev, reference_layout(), nkeys, prf, MODE_FUSED, out_dev, stream);
 }
 
 bool is_pinned_host(const void *ptr)
@@ -509,7 +641,7 @@ int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n)
     return B200DPF_OK;
 }
 
-size_t b200dpf_key_packed_size(int depth) { return depth >= 1 && depth <= 32 ? (size_t)24 + 64u * (size_t)depth : 0; }
+size_t b200dpf_key_packed_size(int depth) { return depth >= 1 && depth <= 32 ? (size_t)32 + 64u * (size_t)depth : 0; }
 
 int b200dpf_key_pack(const int32_t *key, uint8_t *out, size_t out_cap, size_t *written)
 {
@@ -519,12 +651,12 @@ int b200dpf_key_pack(const int32_t *key, uint8_t *out, size_t out_cap, size_t *w
     const size_t need = b200dpf_key_packed_size(depth);
     if (out_cap < need) return fail(B200DPF_EINVAL, "key_pack: need %zu bytes, have %zu", need, out_cap);
     const uint8_t *k = reinterpret_cast<const uint8_t *>(key);
-    std::memcpy(out, "DPF1", 4);
+    std::memset(out, 0, 16);
+    std::memcpy(out, "DPF2", 4);
     out[4] = (uint8_t)depth;
-    out[5] = out[6] = out[7] = 0;
-    std::memcpy(out + 8, k + 16 * host::SLOT_ROOT, 16);
+    std::memcpy(out + 16, k + 16 * host::SLOT_ROOT, 16);
     for (int L = 0; L < depth; L++) {
-        uint8_t *o = out + 24 + 64 * L;
+        uint8_t *o = out + 32 + 64 * L;
         std::memcpy(o, k + 16 * (host::SLOT_CW1 + 2 * L), 32);
         std::memcpy(o + 32, k + 16 * (host::SLOT_CW2 + 2 * L), 32);
     }
@@ -535,16 +667,18 @@ int b200dpf_key_pack(const int32_t *key, uint8_t *out, size_t out_cap, size_t *w
 int b200dpf_key_unpack(const uint8_t *in, size_t in_len, int32_t *key)
 {
     if (!in || !key) return fail(B200DPF_EINVAL, "null buffer");
-    if (in_len < 24 || std::memcmp(in, "DPF1", 4) != 0) return fail(B200DPF_EINVAL, "key_unpack: bad header");
+    if (in_len < 32 || std::memcmp(in, "DPF2", 4) != 0) return fail(B200DPF_EINVAL, "key_unpack: bad header");
     const int depth = in[4];
-    if (depth < 1 || depth > 32 || in[5] || in[6] || in[7] || in_len != b200dpf_key_packed_size(depth))
+    bool pad_zero = true;
+    for (int i = 5; i < 16; i++) pad_zero = pad_zero && in[i] == 0;
+    if (depth < 1 || depth > 32 || !pad_zero || in_len != b200dpf_key_packed_size(depth))
         return fail(B200DPF_EINVAL, "key_unpack: depth %d does not match %zu bytes", depth, in_len);
     std::memset(key, 0, sizeof(int32_t) * host::KEY_WORDS);
     uint8_t *k = reinterpret_cast<uint8_t *>(key);
     k[16 * host::SLOT_DEPTH] = (uint8_t)depth;
-    std::memcpy(k + 16 * host::SLOT_ROOT, in + 8, 16);
+    std::memcpy(k + 16 * host::SLOT_ROOT, in + 16, 16);
     for (int L = 0; L < depth; L++) {
-        const uint8_t *o = in + 24 + 64 * L;
+        const uint8_t *o = in + 32 + 64 * L;
         std::memcpy(k + 16 * (host::SLOT_CW1 + 2 * L), o, 32);
         std::memcpy(k + 16 * (host::SLOT_CW2 + 2 * L), o + 32, 32);
     }
@@ -601,7 +735,20 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     } while (0)
 
     CTX_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CTX_TRY(cudaDeviceGetAttribute(&c->coop_ok, cudaDevAttrCooperativeLaunch, device));
     CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CTX_TRY(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    CTX_TRY(cudaMalloc(&c->d_gridbar, sizeof(uint32_t)));
+    /* the environment is consulted here and nowhere else (b200dpf_ctx_set_option changes a
+     * live context) */
+    c->knobs.leaf_cache = env_int("B200DPF_LEAF_CACHE", c->knobs.leaf_cache);
+    c->knobs.leaf_cache_mb = env_int("B200DPF_LEAF_CACHE_MB", c->knobs.leaf_cache_mb);
+    c->knobs.lane_split = env_int("B200DPF_LANE_SPLIT", c->knobs.lane_split);
+    c->knobs.frontier = env_int("B200DPF_FRONTIER", c->knobs.frontier);
+    c->knobs.frontier_mb = env_int("B200DPF_FRONTIER_MB", c->knobs.frontier_mb);
+    c->knobs.subtree_log2 = env_int("B200DPF_S", c->knobs.subtree_log2);
+    c->knobs.mac_tma = env_int("B200DPF_MAC_TMA", c->knobs.mac_tma);
+    c->knobs.one_launch = env_int("B200DPF_ONE_LAUNCH", c->knobs.one_launch);
     CTX_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
     CTX_TRY(upload_aes_table(host::aes_te0()));
 
@@ -609,6 +756,19 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
      * then permute on the device into breadth-first leaf order, padded to
      * 64-byte rows.  dpf_wrapper.cu:103-115 does the analogous reorder on the
      * host with one ATen call per element. */
+    {   /* a device-resident table may still be being written on the caller's stream (e.g. a dtype
+         * cast enqueued just before this call): our copy runs on a private non-blocking stream,
+         * so wait for the producing device first */
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, table) == cudaSuccess &&
+            (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+            if (attr.device != device) cudaSetDevice(attr.device);
+            const cudaError_t es = cudaDeviceSynchronize();
+            if (attr.device != device) cudaSetDevice(device);
+            CTX_TRY(es);
+        }
+        cudaGetLastError();
+    }
     const size_t row_bytes = (size_t)entry_size * sizeof(int32_t);
     const size_t stage_bytes = (size_t)c->n_local * row_bytes;
     const size_t table_bytes = (size_t)c->n_local * (size_t)c->entry_pad * sizeof(int32_t);
@@ -677,6 +837,9 @@ int b200dpf_destroy(b200dpf_ctx *c)
     if (c->d_keys) cudaFree(c->d_keys);
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_top_counters) cudaFree(c->d_top_counters);
+    if (c->d_gridbar) cudaFree(c->d_gridbar);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->d_frontier) cudaFree(c->d_frontier);
     if (c->d_leaf_cache) cudaFree(c->d_leaf_cache);
     if (c->h_keys) cudaFreeHost(c->h_keys);
@@ -687,22 +850,22 @@ int b200dpf_destroy(b200dpf_ctx *c)
     return B200DPF_OK;
 }
 
-int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, int32_t *out)
+/* Host buffers in and out: keys (either layout) -> pinned staging if pageable -> H2D, the
+ * evaluation, D2H, one stream synchronisation. */
+static int eval_host(b200dpf_ctx *c, const void *keys, size_t key_bytes, const KeyLayout &kl, int64_t nkeys, int prf,
+                     int32_t *out)
 {
-    int rc = check_eval_args(c, keys, nkeys, prf, out);
-    if (rc) return rc;
-    for (int64_t b = 0; b < nkeys; b++)
-        if (host::key_n(keys + b * host::KEY_WORDS) != c->n)
-            return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
-                        (long long)host::key_n(keys + b * host::KEY_WORDS), (long long)c->n);
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
-    if ((size_t)nkeys > c->keys_cap) {
+    int rc;
+    const size_t keys_cap_bytes = c->keys_cap * host::KEY_WORDS * sizeof(int32_t);
+    if (key_bytes > keys_cap_bytes) {
         if (c->d_keys) cudaFree(c->d_keys);
         c->d_keys = nullptr;
         c->keys_cap = 0;
-        CUDA_TRY(cudaMalloc(&c->d_keys, (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t)));
-        c->keys_cap = (size_t)nkeys;
+        const size_t cap_keys = (key_bytes + host::KEY_WORDS * sizeof(int32_t) - 1) / (host::KEY_WORDS * sizeof(int32_t));
+        CUDA_TRY(cudaMalloc(&c->d_keys, cap_keys * host::KEY_WORDS * sizeof(int32_t)));
+        c->keys_cap = cap_keys;
     }
     const size_t out_elems = (size_t)nkeys * c->entry_size;
     if (out_elems > c->out_cap) {
@@ -714,10 +877,9 @@ int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, in
     }
     /* pageable host memory goes through the context's pinned staging so both copies are real
      * asynchronous DMA transfers; already-pinned buffers (ours or the caller's) are used as is */
-    const size_t key_bytes = (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t);
-    const int32_t *src = keys;
+    const void *src = keys;
     if (!is_pinned_host(keys)) {
-        rc = ensure_host_keys(c, nkeys);
+        rc = ensure_host_keys(c, (int64_t)((key_bytes + host::KEY_WORDS * sizeof(int32_t) - 1) / (host::KEY_WORDS * sizeof(int32_t))));
         if (rc) return rc;
         std::memcpy(c->h_keys, keys, key_bytes);
         src = c->h_keys;
@@ -734,13 +896,41 @@ int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, in
         }
         dst = c->h_out;
     }
+    /* the previous evaluation may have run on a caller's stream: the staging copy below must not
+     * overtake it (run_pipeline orders the kernels, this orders the H2D) */
+    if (c->has_last && c->last_stream != c->stream) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
     CUDA_TRY(cudaMemcpyAsync(c->d_keys, src, key_bytes, cudaMemcpyHostToDevice, c->stream));
-    rc = run_eval(c, c->d_keys, nkeys, prf, c->d_out, c->stream);
+    rc = run_pipeline(c, c->d_keys, kl, nkeys, prf, MODE_FUSED, c->d_out, c->stream);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(dst, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (dst != out) std::memcpy(out, dst, out_elems * sizeof(int32_t));
     return B200DPF_OK;
+}
+
+int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, int32_t *out)
+{
+    int rc = check_eval_args(c, keys, nkeys, prf, out);
+    if (rc) return rc;
+    for (int64_t b = 0; b < nkeys; b++)
+        if (host::key_n(keys + b * host::KEY_WORDS) != c->n)
+            return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
+                        (long long)host::key_n(keys + b * host::KEY_WORDS), (long long)c->n);
+    return eval_host(c, keys, (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t), reference_layout(), nkeys, prf, out);
+}
+
+int b200dpf_eval_packed(b200dpf_ctx *c, const uint8_t *packed, int64_t nkeys, int prf, int32_t *out)
+{
+    int rc = check_eval_args(c, packed, nkeys, prf, out);
+    if (rc) return rc;
+    const size_t stride = b200dpf_key_packed_size(c->depth);
+    for (int64_t b = 0; b < nkeys; b++) {
+        const uint8_t *k = packed + (size_t)b * stride;
+        if (std::memcmp(k, "DPF2", 4) != 0 || k[4] != (uint8_t)c->depth)
+            return fail(B200DPF_EINVAL, "packed key %lld: bad header or depth %d, table has depth %d (n=%lld)", (long long)b,
+                        (int)k[4], c->depth, (long long)c->n);
+    }
+    return eval_host(c, packed, (size_t)nkeys * stride, compact_layout(c->depth), nkeys, prf, out);
 }
 
 int b200dpf_host_staging(b200dpf_ctx *c, int64_t nkeys, int32_t **keys_pinned)
@@ -769,7 +959,8 @@ int b200dpf_eval_device_acc(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys,
     if (rc) return rc;
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
-    return run_pipeline(c, keys_dev, nkeys, prf, MODE_FUSED, out_dev, reinterpret_cast<cudaStream_t>(cuda_stream), false);
+    return run_pipeline(c, keys_dev, reference_layout(), nkeys, prf, MODE_FUSED, out_dev,
+                        reinterpret_cast<cudaStream_t>(cuda_stream), false);
 }
 
 int b200dpf_expand_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int prf, void *shares_dev, void *cuda_stream)
@@ -779,7 +970,8 @@ int b200dpf_expand_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, i
     if (c->shard_count != 1) return fail(B200DPF_ESTATE, "expand needs an unsharded context");
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
-    return run_pipeline(c, keys_dev, nkeys, prf, MODE_EXPAND, shares_dev, reinterpret_cast<cudaStream_t>(cuda_stream));
+    return run_pipeline(c, keys_dev, reference_layout(), nkeys, prf, MODE_EXPAND, shares_dev,
+                        reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 int64_t b200dpf_ctx_n(const b200dpf_ctx *c) { return c ? c->n : -1; }
@@ -790,8 +982,26 @@ int b200dpf_ctx_last_launches(const b200dpf_ctx *c) { return c ? c->last_launche
 int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *c, int s)
 {
     if (!c || s < 0 || s > 16) return fail(B200DPF_EINVAL, "subtree log2 out of range");
-    c->s_override = s;
+    c->knobs.subtree_log2 = s;
     return B200DPF_OK;
+}
+
+int b200dpf_ctx_set_option(b200dpf_ctx *c, const char *name, int value)
+{
+    if (!c || !name) return fail(B200DPF_EINVAL, "null argument");
+    struct { const char *name; int *slot; int lo, hi; } opts[] = {
+        {"leaf_cache", &c->knobs.leaf_cache, 0, 1},       {"leaf_cache_mb", &c->knobs.leaf_cache_mb, 1, 1 << 20},
+        {"lane_split", &c->knobs.lane_split, 0, 1},       {"frontier", &c->knobs.frontier, 0, 1},
+        {"frontier_mb", &c->knobs.frontier_mb, 1, 1 << 16}, {"subtree_log2", &c->knobs.subtree_log2, 0, 16},
+        {"mac_tma", &c->knobs.mac_tma, 0, 1},             {"one_launch", &c->knobs.one_launch, 0, 1},
+    };
+    for (auto &o : opts)
+        if (std::strcmp(o.name, name) == 0) {
+            if (value < o.lo || value > o.hi) return fail(B200DPF_EINVAL, "option %s=%d out of range [%d,%d]", name, value, o.lo, o.hi);
+            *o.slot = value;
+            return B200DPF_OK;
+        }
+    return fail(B200DPF_EINVAL, "unknown option '%s'", name);
 }
 
 }  // extern "C"

@@ -154,6 +154,25 @@ at::Tensor eval_gpu_packed(const at::Tensor &keys, const std::vector<void *> &bu
     return result;
 }
 
+/* keys in the compact wire form (key_pack), concatenated: uint8 CPU tensor [B * packed_size] or
+ * [B, packed_size] -> int32[B,E] CPU tensor.  The buffer is copied to the device as it is. */
+at::Tensor eval_gpu_compact(const at::Tensor &packed, int64_t nkeys, const std::vector<void *> &buffers, int prf)
+{
+    b200dpf_ctx *ctx = ctx_of(buffers);
+    TORCH_CHECK(packed.device().is_cpu() && packed.scalar_type() == at::kByte && packed.is_contiguous(),
+                "eval_gpu_compact: packed keys must be a contiguous CPU uint8 tensor");
+    int depth = 0;
+    for (int64_t n = b200dpf_ctx_n(ctx); n > 1; n >>= 1) depth++;
+    TORCH_CHECK(nkeys >= 1 && (int64_t)packed.numel() == nkeys * (int64_t)b200dpf_key_packed_size(depth),
+                "eval_gpu_compact: expected ", nkeys, " keys of ", b200dpf_key_packed_size(depth), " bytes");
+    at::Tensor result = torch::empty({nkeys, (int64_t)b200dpf_ctx_entry_size(ctx)}, at::kInt);
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_eval_packed(ctx, packed.data_ptr<uint8_t>(), nkeys, prf, result.data_ptr<int32_t>()), "eval_gpu");
+    }
+    return result;
+}
+
 /* keys as a Python list of int32[524] CPU tensors, any length -> int32[len, E] CPU tensor
  * (packing done here, not with torch.stack in Python) */
 at::Tensor eval_gpu_list(const std::vector<at::Tensor> &keys, const std::vector<void *> &buffers, int prf)
@@ -225,6 +244,11 @@ void set_subtree_log2(const std::vector<void *> &buffers, int s)
     check(b200dpf_ctx_set_subtree_log2(ctx_of(buffers), s), "set_subtree_log2");
 }
 
+void set_option(const std::vector<void *> &buffers, const std::string &name, int value)
+{
+    check(b200dpf_ctx_set_option(ctx_of(buffers), name.c_str(), value), "set_option");
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
@@ -261,4 +285,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("expand_gpu_device", &expand_gpu_device, "device-resident share-vector expansion");
     m.def("last_launches", &last_launches);
     m.def("set_subtree_log2", &set_subtree_log2);
+    m.def("set_option", &set_option, "tuning knob of a live context (include/b200dpf.h: b200dpf_ctx_set_option)");
+    m.def("eval_gpu_compact", &eval_gpu_compact, "eval_gpu with keys in the compact wire form (uint8 tensor)");
+    m.def("key_packed_size", [](int depth) { return (int64_t)b200dpf_key_packed_size(depth); });
 }

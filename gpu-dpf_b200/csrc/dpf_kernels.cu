@@ -34,11 +34,16 @@
  *                 so lookups are conflict-free, and the shared address of a
  *                 lookup is formed by ONE PRMT (byte insert into a 64 KiB-aligned
  *                 base) + the LDS immediate offset.
- *   frontier    = an optional first launch (MODE_FRONTIER) expands the top of every
- *                 key's tree once and stores the seeds of all depth-F nodes; the
- *                 main launch then starts each work item from its frontier node
- *                 instead of re-walking from the root, so work items can be small
+ *   frontier    = the top of every key's tree is expanded once and the seeds of all
+ *                 depth-F nodes stored; work items then start from their frontier
+ *                 node instead of re-walking from the root, so items can be small
  *                 (good load balance) without paying a root-to-subtree walk each.
+ *   one launch  = a whole evaluation is ONE cooperative launch: phase `top` clears the
+ *                 result and the ticket counters and builds the frontier, a grid-wide
+ *                 barrier follows, phase `main` does the work and block 0 re-arms the
+ *                 top-phase tickets for the next launch.  (The reference's step is
+ *                 cudaMemcpy + kernel + cudaMemcpy with a stream created per call,
+ *                 dpf_wrapper.cu:150-176; ours was memset, memset, kernel, kernel.)
  *   wide rows   = NV uint4 of a table row per pass (16/32/64 int32 columns): the
  *                 first 64 bytes of both rows are prefetched before the leaf
  *                 expansion, the rest streamed chunk by chunk during the MAC.
@@ -48,6 +53,8 @@
  *                 red.global.add.u32.
  */
 #include "dpf_kernels.cuh"
+
+#include <atomic>
 
 #include "dpf_core.cuh"
 
@@ -189,11 +196,34 @@ template <int NV> struct KernelShape<PRF_AES128, NV> { enum { THREADS = (NV <= 8
 
 extern __shared__ __align__(16) unsigned char g_dyn_smem[];
 
-template <int PRF, int NV, int MODE>
-__global__ void __launch_bounds__((KernelShape<PRF, NV>::THREADS), (KernelShape<PRF, NV>::MIN_BLOCKS))
-dpf_eval_kernel(const __grid_constant__ EvalParams p)
+/* Grid-wide barrier of a cooperative launch (every block is resident, so spinning cannot
+ * deadlock).  `bar` only ever counts up; `target` is the value it has once every block of THIS
+ * launch has arrived (the host keeps the running total), compared wrap-safe. */
+__device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t target)
 {
-    constexpr int THREADS = KernelShape<PRF, NV>::THREADS;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        for (uint32_t spin = 0;; spin++) {
+            uint32_t v;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if ((int32_t)(v - target) >= 0) break;
+            if (spin > (1u << 25)) __trap();   /* a lost arrival must not hang the GPU */
+            __nanosleep(40);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+/* One traversal phase of a launch: every block walks the key groups (starting at its own offset so
+ * blocks spread over groups), loads a group's correction words into shared memory when the group
+ * still has tickets, and its warps draw work items until the group runs dry. */
+template <int PRF, int NV, int THREADS, int MODE>
+__device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams &ph,
+                                          const typename TablePolicy<PRF>::type &ta)
+{
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
@@ -207,37 +237,23 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
     const int spw_log2 = 5 - p.kpw_log2;
     const int kslot = lane & (kpw - 1);
     const uint32_t sslot = (uint32_t)lane >> p.kpw_log2;
-    const uint32_t ntickets = p.nsub >> spw_log2;
+    const uint32_t ntickets = ph.nsub >> spw_log2;
 
     DevEnv<PRF, NV, THREADS, MODE> env;
+    env.ta = ta;
     env.cw_lane = cw_s + kslot;
     env.cwlo_lane = cwlo_s + kslot;
     env.kpw = (uint32_t)kpw;
     env.stack_lo = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_stack_lo) + tid;
-    env.stack_hi = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_stack_hi) + tid - p.stack_split * THREADS;
-    env.stack_split = p.stack_split;
+    env.stack_hi = reinterpret_cast<uint4 *>(g_dyn_smem + p.off_stack_hi) + tid - ph.stack_split * THREADS;
+    env.stack_split = ph.stack_split;
     env.row_stride_v = p.row_stride_v;
     env.depth = p.depth;
-
-    if constexpr (PRF == PRF_AES128) {
-        /* replicate Te0..Te3 across the 32 banks: entry v, lane L */
-        const uint32_t tab = (uint32_t)__cvta_generic_to_shared(g_dyn_smem + p.off_tab);
-        if ((tab & 0xffffu) != 0) __trap();   /* layout contract with the host planner */
-        for (int i = tid; i < 256 * 32; i += THREADS) {
-            const uint32_t v = c_te0[i >> 5];
-            unsigned char *e = g_dyn_smem + p.off_tab + (i >> 5) * 256 + (i & 31) * 4;
-            *reinterpret_cast<uint32_t *>(e) = v;
-            *reinterpret_cast<uint32_t *>(e + 128) = __funnelshift_l(v, v, 8);
-            *reinterpret_cast<uint32_t *>(e + 65536) = __funnelshift_l(v, v, 16);
-            *reinterpret_cast<uint32_t *>(e + 65536 + 128) = __funnelshift_l(v, v, 24);
-        }
-        env.ta.lanebase = tab + lane * 4;
-    }
 
     for (int j = 0; j < p.key_groups; j++) {
         const int kg = (int)((blockIdx.x + (unsigned)j) % (unsigned)p.key_groups);
 
-        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(p.counters + kg) < ntickets) ? 1 : 0;
+        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(ph.counters + kg) < ntickets) ? 1 : 0;
         __syncthreads();
         const bool has_work = (*flag_s != 0);
         if (has_work) {
@@ -250,15 +266,17 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
                 const int lb = e - bank * (p.depth * 2);   /* 2*level + bit       */
                 int key = kg * kpw + k;
                 if (key >= p.nkeys) key = p.nkeys - 1;
-                const uint4 v = __ldg(p.keys + (size_t)key * 131 + (bank ? 65 : 1) + lb);
                 const int level = lb >> 1, bit = lb & 1;
+                const uint32_t slot = p.key_compact ? 2u + 4u * (uint32_t)level + 2u * (uint32_t)bank + (uint32_t)bit
+                                                    : (bank ? 65u : 1u) + (uint32_t)lb;
+                const uint4 v = __ldg(p.keys + (size_t)key * p.key_stride_v + slot);
                 cw_s[((level * 2 + bank) * 2 + bit) * 32 + k] = v;
                 if (level == 0) cwlo_s[(bank * 2 + bit) * 32 + k] = v.x;
             }
             if (tid < kpw) {
                 int key = kg * kpw + tid;
                 if (key >= p.nkeys) key = p.nkeys - 1;
-                root_s[tid] = __ldg(p.keys + (size_t)key * 131 + 129);
+                root_s[tid] = __ldg(p.keys + (size_t)key * p.key_stride_v + p.key_root_v);
             }
         }
         __syncthreads();
@@ -277,25 +295,27 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
 
         for (;;) {
             uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(p.counters + kg, 1u);
+            if (lane == 0) t = atomicAdd(ph.counters + kg, 1u);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= ntickets) break;
             const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
-            if (p.frontier_in != nullptr) {
-                const uint4 fv = p.frontier_in[((size_t)kg * p.nfront + (q >> p.front_shift)) * kpw + kslot];
+            if (ph.frontier_in != nullptr) {
+                /* written earlier in this launch (before the grid barrier) or by the previous one:
+                 * read through L2, never a stale L1 line */
+                const uint4 fv = __ldcg(ph.frontier_in + ((size_t)kg * p.nfront + (q >> ph.front_shift)) * kpw + kslot);
                 start = make_seed(fv.x, fv.y, fv.z, fv.w);
             }
-            const Seed r = walk_down<PRF>(env, start, p.walk_first_level, p.walk_steps, p.sub_first + q);
+            const Seed r = walk_down<PRF>(env, start, ph.walk_first_level, ph.walk_steps, ph.sub_first + q);
             if (MODE == MODE_FRONTIER) {
-                env.front_out = p.frontier_out + ((size_t)kg * p.nfront + ((size_t)q << p.s)) * kpw + kslot;
-                eval_subtree<PRF, true>(env, r, p.s, p.level_base);
+                env.front_out = p.frontier_out + ((size_t)kg * p.nfront + ((size_t)q << ph.s)) * kpw + kslot;
+                eval_subtree<PRF, true>(env, r, ph.s, ph.level_base);
             } else {
-                env.rows = p.table + ((size_t)q << p.s) * p.row_stride_v + p.col_off_v;
-                env.pos_base = (p.sub_first + q) << p.s;
-                env.leaf_out = p.leaf_cache ? p.leaf_cache + ((size_t)kg * p.n_local + ((size_t)q << p.s)) * 32 + lane
+                env.rows = p.table + ((size_t)q << ph.s) * p.row_stride_v + p.col_off_v;
+                env.pos_base = (ph.sub_first + q) << ph.s;
+                env.leaf_out = p.leaf_cache ? p.leaf_cache + ((size_t)kg * p.n_local + ((size_t)q << ph.s)) * 32 + lane
                                             : nullptr;
-                eval_subtree<PRF, false>(env, r, p.s, 0);
+                eval_subtree<PRF, false>(env, r, ph.s, 0);
             }
         }
 
@@ -315,6 +335,45 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
         }
         __syncthreads();   /* everyone done with this group's correction words */
     }
+}
+
+template <int PRF, int NV, int MODE>
+__global__ void __launch_bounds__((KernelShape<PRF, NV>::THREADS), (KernelShape<PRF, NV>::MIN_BLOCKS))
+dpf_eval_kernel(const __grid_constant__ EvalParams p)
+{
+    constexpr int THREADS = KernelShape<PRF, NV>::THREADS;
+    const int tid = threadIdx.x;
+
+    typename TablePolicy<PRF>::type ta;
+    if constexpr (PRF == PRF_AES128) {
+        /* replicate Te0..Te3 across the 32 banks: entry v, lane L */
+        const uint32_t tab = (uint32_t)__cvta_generic_to_shared(g_dyn_smem + p.off_tab);
+        if ((tab & 0xffffu) != 0) __trap();   /* layout contract with the host planner */
+        for (int i = tid; i < 256 * 32; i += THREADS) {
+            const uint32_t v = c_te0[i >> 5];
+            unsigned char *e = g_dyn_smem + p.off_tab + (i >> 5) * 256 + (i & 31) * 4;
+            *reinterpret_cast<uint32_t *>(e) = v;
+            *reinterpret_cast<uint32_t *>(e + 128) = __funnelshift_l(v, v, 8);
+            *reinterpret_cast<uint32_t *>(e + 65536) = __funnelshift_l(v, v, 16);
+            *reinterpret_cast<uint32_t *>(e + 65536 + 128) = __funnelshift_l(v, v, 24);
+        }
+        ta.lanebase = tab + (tid & 31) * 4;
+    }
+
+    if constexpr (MODE != MODE_FRONTIER) {
+        if (p.fuse_top) {
+            /* single-launch pipeline: clear this launch's accumulators and main-phase tickets,
+             * expand the top of every key's tree into the frontier, meet at the grid barrier */
+            const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + tid, gthreads = (uint64_t)gridDim.x * THREADS;
+            for (uint64_t i = gtid; i < p.zero_a_words; i += gthreads) p.zero_a[i] = 0u;
+            for (uint64_t i = gtid; i < p.zero_b_words; i += gthreads) p.zero_b[i] = 0u;
+            if (p.top.nsub != 0) run_phase<PRF, 4, THREADS, MODE_FRONTIER>(p, p.top, ta);
+            grid_barrier(p.grid_bar, p.grid_bar_target);
+            if (blockIdx.x == 0)   /* nobody draws top-phase tickets any more: re-arm them for the next launch */
+                for (uint32_t i = tid; i < p.rearm_words; i += THREADS) p.rearm[i] = 0u;
+        }
+    }
+    run_phase<PRF, NV, THREADS, MODE>(p, p.main, ta);
 }
 
 /* MAC-only pass for wide entries: leaves come from the cache written by the first fused
@@ -538,18 +597,24 @@ template <int PRF, int NV, int MODE>
 cudaError_t launch_one(const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
 {
     auto kern = dpf_eval_kernel<PRF, NV, MODE>;
-    /* function attributes are per device and sticky: set them once per (device, size) */
-    static int configured[64];   /* smem bytes + 1 last configured on each device, 0 = never */
+    /* function attributes are per device and sticky: set them once per (device, size); contexts
+     * on different host threads may race here, hence the atomics (a duplicate set is harmless) */
+    static std::atomic<int> configured[64];   /* smem bytes + 1 last configured on each device, 0 = never */
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || configured[dev] != (int)smem + 1) {
+    if (dev < 0 || dev >= 64 || configured[dev].load(std::memory_order_acquire) != (int)smem + 1) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         /* the kernels live in shared memory; L1 only sees broadcast table rows */
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) configured[dev] = (int)smem + 1;
+        if (dev >= 0 && dev < 64) configured[dev].store((int)smem + 1, std::memory_order_release);
+    }
+    if (p.fuse_top) {
+        void *args[] = {const_cast<EvalParams *>(&p)};
+        return cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(kern), dim3((unsigned)grid),
+                                           dim3((unsigned)(KernelShape<PRF, NV>::THREADS)), args, smem, stream);
     }
     kern<<<grid, (KernelShape<PRF, NV>::THREADS), smem, stream>>>(p);
     return cudaGetLastError();
@@ -649,8 +714,15 @@ cudaError_t launch_mac_tma(const MacParams &p, int grid, cudaStream_t stream)
 {
     typedef MacTmaShape<16> S;
     auto kern = dpf_mac_tma_kernel<16>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
+    static std::atomic<int> configured[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev].store(1, std::memory_order_release);
+    }
     kern<<<grid, (int)S::THREADS, (int)S::SMEM, stream>>>(p);
     return cudaGetLastError();
 }

@@ -9,9 +9,32 @@
 
 namespace b200dpf {
 
+/* One traversal phase of a launch: which subtrees the work items are, where an item starts and
+ * which ticket counters hand the items out. */
+struct PhaseParams {
+    int s;                    /* log2 leaves per work item (one warp = 32 keys x 2^s)   */
+    /* where a work item starts: the key's root seed, or a node of a precomputed
+     * frontier (seeds of every depth-F node of this shard)                            */
+    const uint4 *frontier_in; /* [key_groups][nfront][kpw keys] or null                 */
+    int front_shift;          /* work item q starts at frontier node q >> front_shift   */
+    int walk_first_level;     /* correction-word level of the first walk step           */
+    int walk_steps;           /* walk steps from the start node to the subtree root     */
+    int level_base;           /* level of the subtree's bottom expansion (0 = leaves)   */
+    uint32_t sub_first;       /* breadth-first index of the shard's first 2^s-subtree   */
+    uint32_t nsub;            /* number of 2^s-subtrees in this shard                   */
+    uint32_t *counters;       /* [key_groups] tickets, zero at phase start; one ticket =
+                                 32/kpw consecutive subtrees for the group's kpw keys   */
+    int stack_split;          /* pending-sibling stack levels [0, split) live in the lo
+                                 region, the rest in the hi region                      */
+};
+
 /* Parameters of one evaluation launch (one pass over <= 16*NVMAX columns). */
 struct EvalParams {
-    const uint4 *keys;        /* [nkeys][131] 128-bit slots, reference wire format      */
+    const uint4 *keys;        /* [nkeys] keys, key_stride_v 128-bit slots apart          */
+    uint32_t key_stride_v;    /* reference wire format: 131; compact: 2 + 4*depth        */
+    uint32_t key_root_v;      /* slot of the root seed: 129 (reference) / 1 (compact)    */
+    int key_compact;          /* 0: cw_1 at slots 1.., cw_2 at 65.. (dpf_wrapper.cu:26-46);
+                                 1: slot 2 + 4*level + 2*bank + bit                      */
     int nkeys;
     int kpw_log2;             /* log2 keys per warp (5 = one key per lane).  With fewer
                                  keys than lanes the spare lanes take further subtrees of
@@ -21,25 +44,29 @@ struct EvalParams {
     const uint4 *table;       /* this shard's rows in breadth-first leaf order          */
     uint32_t row_stride_v;    /* uint4 per table row (padded entry size / 4)            */
     uint32_t col_off_v;       /* first uint4 column of this pass                        */
-    uint32_t *out;            /* [nkeys][out_stride] uint32, pre-zeroed                 */
+    uint32_t *out;            /* [nkeys][out_stride] uint32, zero before the main phase  */
     uint32_t out_stride;
     uint32_t col_off;         /* first int32 column of this pass                        */
     uint32_t ncols;           /* valid int32 columns in this pass (<= 4*NV)             */
     int depth;                /* log2 n                                                 */
-    int s;                    /* log2 leaves per work item (one warp = 32 keys x 2^s)   */
-    /* where a work item starts: the key's root seed, or a node of a precomputed
-     * frontier (seeds of every depth-F node of this shard, built by MODE 2)           */
-    const uint4 *frontier_in; /* [key_groups][nfront][kpw keys] or null                 */
-    uint4 *frontier_out;      /* MODE 2 output, same layout                             */
+    PhaseParams main;         /* the phase that produces the result (or, in the stand-alone
+                                 frontier kernel, the frontier)                          */
+    /* single-launch pipeline: the launch first clears its own accumulators and ticket
+     * counters and expands the top of every key's tree into the frontier (phase `top`,
+     * full seeds), crosses a grid-wide barrier (cooperative launch, every block resident)
+     * and then runs `main` from the frontier nodes.                                      */
+    int fuse_top;             /* 1: run `top`, barrier, then `main`                      */
+    PhaseParams top;
+    uint32_t *zero_a;         /* words cleared before the barrier: the result ...        */
+    uint64_t zero_a_words;
+    uint32_t *zero_b;         /* ... and the main-phase ticket counters                  */
+    uint64_t zero_b_words;
+    uint32_t *rearm;          /* top-phase tickets, cleared AFTER the barrier for the next launch */
+    uint32_t rearm_words;
+    uint32_t *grid_bar;       /* monotonic arrival counter of the context               */
+    uint32_t grid_bar_target; /* value it reaches when every block of this launch arrived */
+    uint4 *frontier_out;      /* frontier written by `top` (or by the stand-alone kernel) */
     uint32_t nfront;          /* frontier nodes per key (this shard)                    */
-    int front_shift;          /* work item q starts at frontier node q >> front_shift   */
-    int walk_first_level;     /* correction-word level of the first walk step           */
-    int walk_steps;           /* walk steps from the start node to the subtree root     */
-    int level_base;           /* level of the subtree's bottom expansion (0 = leaves)   */
-    uint32_t sub_first;       /* breadth-first index of the shard's first 2^s-subtree   */
-    uint32_t nsub;            /* number of 2^s-subtrees in this shard                   */
-    uint32_t *counters;       /* [key_groups] tickets, pre-zeroed; one ticket = 32/kpw
-                                 consecutive subtrees for the group's kpw keys          */
     /* wide entries: the first pass also stores every leaf's low word, [key group][leaf
      * position][32 keys], so further column blocks are MAC-only (launch_mac)          */
     uint32_t *leaf_cache;
@@ -54,7 +81,6 @@ struct EvalParams {
     uint32_t off_flag;        /* int                                                    */
     uint32_t off_stack_lo;    /* pending-sibling stack, levels [0, stack_split)         */
     uint32_t off_stack_hi;    /* levels [stack_split, s-1)                              */
-    int stack_split;
     uint32_t off_tab;         /* AES tables: 128 KiB whose shared-window address is a
                                  multiple of 64 KiB                                     */
 };
@@ -76,7 +102,8 @@ cudaError_t upload_aes_table(const uint32_t *te0_256);
 
 /* One pass of the fused evaluation (mode 0), the share expansion (mode 1) or the
  * frontier build (mode 2; nv must be 4 for modes 1 and 2).
- * grid = number of persistent blocks; smem_bytes = dynamic shared memory. */
+ * grid = number of persistent blocks; smem_bytes = dynamic shared memory.  With p.fuse_top the
+ * launch is cooperative (every block resident), which the in-kernel grid barrier relies on. */
 cudaError_t launch_eval(int prf, int nv, int mode, const EvalParams &p, int grid, size_t smem_bytes,
                         cudaStream_t stream);
 

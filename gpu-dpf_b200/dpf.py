@@ -137,6 +137,19 @@ class DPF(object):
             return torch.zeros((0, self.table_effective_entry_size), dtype=torch.int32)
         return dpf_cpp.eval_gpu_list(list(keys), self.buffers, self.prf_method)
 
+    def pack_keys(self, keys):
+        """Compact wire form of a batch (24% to 56% smaller than int32[524] keys, depending on n): one
+        contiguous uint8 tensor [B, 32 + 64*depth], pinned when CUDA is available, for eval_gpu_compact."""
+        blobs = [dpf_cpp.key_pack(k) for k in keys]
+        t = torch.frombuffer(bytearray(b"".join(blobs)), dtype=torch.uint8).reshape(len(blobs), -1)
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+    def eval_gpu_compact(self, packed):
+        """eval_gpu for keys in the compact wire form (pack_keys): the packed bytes are what crosses PCIe."""
+        if self.buffers is None:
+            raise Exception("Must call `eval_init` before `eval_gpu`")
+        return dpf_cpp.eval_gpu_compact(packed.contiguous(), packed.shape[0], self.buffers, self.prf_method)
+
     def eval_gpu_device(self, keys_dev, out_dev=None, out_ptr=None, accumulate=False):
         """Device-resident, asynchronous variant: keys_dev int32 [B,524] CUDA tensor ->
         int32 [B, entry_size] CUDA tensor, enqueued on the current torch stream.
@@ -144,12 +157,19 @@ class DPF(object):
         then be a raw (e.g. peer-mapped) device address."""
         if self.buffers is None:
             raise Exception("Must call `eval_init` before `eval_gpu`")
-        assert keys_dev.is_cuda and keys_dev.dtype == torch.int32 and keys_dev.is_contiguous()
+        if not (keys_dev.is_cuda and keys_dev.dtype == torch.int32 and keys_dev.is_contiguous() and keys_dev.dim() == 2
+                and keys_dev.shape[1] == 524 and keys_dev.device.index == self.device):
+            raise Exception("keys_dev must be a contiguous int32 [B, 524] tensor on cuda:%d" % self.device)
         stream = torch.cuda.current_stream(keys_dev.device).cuda_stream
         if out_ptr is None:
             if out_dev is None:
                 out_dev = torch.empty((keys_dev.shape[0], self.table_effective_entry_size), dtype=torch.int32,
                                       device=keys_dev.device)
+            elif not (out_dev.is_cuda and out_dev.dtype == torch.int32 and out_dev.is_contiguous()
+                      and out_dev.device == keys_dev.device
+                      and tuple(out_dev.shape) == (keys_dev.shape[0], self.table_effective_entry_size)):
+                raise Exception("out_dev must be a contiguous int32 [%d, %d] tensor on %s"
+                                % (keys_dev.shape[0], self.table_effective_entry_size, keys_dev.device))
             out_ptr = out_dev.data_ptr()
         dpf_cpp.eval_gpu_device(keys_dev.data_ptr(), keys_dev.shape[0], self.buffers, self.prf_method,
                                 out_ptr, stream, accumulate)
@@ -228,7 +248,7 @@ def _next_pow2(n):
 def _pad_rows_to_pow2(table):
     """Zero rows up to the next power of two: they contribute nothing to any inner product."""
     pad = _next_pow2(table.shape[0]) - table.shape[0]
-    return torch.cat([table, torch.zeros((pad, table.shape[1]), dtype=table.dtype)])
+    return torch.cat([table, torch.zeros((pad, table.shape[1]), dtype=table.dtype, device=table.device)])
 
 
 # ---------------------------------------------------------------------------

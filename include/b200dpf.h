@@ -23,6 +23,12 @@
  *
  * The GPU entry points require a CUDA device and fail with B200DPF_ECUDA when
  * none is usable: there is no CPU fallback behind them.
+ *
+ * Threading: a context is NOT re-entrant -- its device scratch (ticket counters, frontier,
+ * leaf cache, key/result staging) serves one evaluation at a time, so calls on one context must
+ * come from one host thread at a time.  Evaluations enqueued on DIFFERENT streams through the
+ * *_device entry points are ordered by the library (each waits for the context's previous
+ * evaluation).  Use one context per concurrent stream of work; contexts are independent.
  */
 #ifndef B200DPF_H
 #define B200DPF_H
@@ -110,11 +116,13 @@ int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n);
 /*
  * Compact wire form of a key.  Of the 131 slots of the
  * reference format only 4*depth correction words, the root seed and the depth are live
- * (dpf_base/dpf.h:18-29 sizes the arrays for n = 2^32).  Packed layout, little endian:
- *   "DPF1" | depth (u8) | 3 zero bytes | root seed (16) | per level L = 0..depth-1:
+ * (dpf_base/dpf.h:18-29 sizes the arrays for n = 2^32).  Packed layout, little endian,
+ * every field 16-byte aligned so the GPU reads it in place (b200dpf_eval_packed):
+ *   "DPF2" | depth (u8) | 11 zero bytes | root seed (16) | per level L = 0..depth-1:
  *   cw_1[2L], cw_1[2L+1], cw_2[2L], cw_2[2L+1] (16 bytes each)
- * = 24 + 64*depth bytes (1304 at n = 2^20 instead of 2096).  unpack() restores the exact
- * int32[524] key (unused slots zero), so packed keys evaluate bit-identically.
+ * = 32 + 64*depth bytes (1312 at n = 2^20, 928 at n = 2^14, instead of 2096).  unpack()
+ * restores the exact int32[524] key (unused slots zero), so packed keys evaluate
+ * bit-identically.
  */
 size_t b200dpf_key_packed_size(int depth);
 int b200dpf_key_pack(const int32_t *key, uint8_t *out, size_t out_cap, size_t *written);
@@ -159,6 +167,15 @@ int b200dpf_destroy(b200dpf_ctx *ctx);
  * reference requires exactly 512).
  */
 int b200dpf_eval(b200dpf_ctx *ctx, const int32_t *keys, int64_t nkeys, int prf, int32_t *out);
+
+/*
+ * Same evaluation with keys in the compact wire form (b200dpf_key_pack): `packed` holds nkeys
+ * keys of this table's depth back to back, b200dpf_key_packed_size(depth) bytes each (host
+ * memory).  The buffer goes to the device as it is and the kernel reads the packed layout, so the
+ * host-to-device copy is 2.3x smaller at n = 2^14 and 1.6x at n = 2^20 than with the
+ * reference's 2096-byte keys (dpf_wrapper.cu:26-46, :150).
+ */
+int b200dpf_eval_packed(b200dpf_ctx *ctx, const uint8_t *packed, int64_t nkeys, int prf, int32_t *out);
 
 /*
  * Pinned (page-locked) host staging owned by the context, sized for `nkeys` keys: callers
@@ -212,6 +229,21 @@ int b200dpf_ctx_last_launches(const b200dpf_ctx *ctx);
 /* Algorithm tuning knob, mainly for tests: log2 of the leaves one thread
  * expands depth-first per work item (0 = automatic). */
 int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *ctx, int s);
+
+/*
+ * Tuning knobs of a live context.  Their defaults come from the environment variables named
+ * below, which are read ONCE, in b200dpf_create.
+ *   "one_launch"    (B200DPF_ONE_LAUNCH, 1)     whole evaluation as one cooperative launch
+ *   "frontier"      (B200DPF_FRONTIER, 1)       expand the top of the tree once per evaluation
+ *   "frontier_mb"   (B200DPF_FRONTIER_MB, 256)  cap on the frontier buffer
+ *   "subtree_log2"  (B200DPF_S, 0 = automatic)  as b200dpf_ctx_set_subtree_log2
+ *   "lane_split"    (B200DPF_LANE_SPLIT, 1)     batches < 32 keys: lane = (key, subtree)
+ *   "leaf_cache"    (B200DPF_LEAF_CACHE, 1)     entry_size > 32: expand once, MAC-only passes
+ *   "leaf_cache_mb" (B200DPF_LEAF_CACHE_MB, 16384)  cap; larger batches run in chunks that fit
+ *   "mac_tma"       (B200DPF_MAC_TMA, 1)        cp.async.bulk-staged MAC passes
+ * Results never depend on them.
+ */
+int b200dpf_ctx_set_option(b200dpf_ctx *ctx, const char *name, int value);
 
 #ifdef __cplusplus
 }

@@ -132,14 +132,16 @@ def test_python_api_cpu_side():
 
 
 def test_compact_key_format(golden):
-    """pack/unpack round-trips every golden key exactly and shrinks it to 24 + 64*depth bytes."""
+    """pack/unpack round-trips every golden key exactly and shrinks it to 32 + 64*depth bytes, every field
+    16-byte aligned (the GPU reads this form in place: b200dpf_eval_packed)."""
     import dpf_cpp
     for ci, (prf, n, alpha, seed32) in enumerate(golden["case_meta"]):
         for keys in (golden["keys_a"], golden["keys_b"]):
             k = keys[ci]
             packed = b200dpf.key_pack(k)
             depth = int(n).bit_length() - 1
-            assert len(packed) == 24 + 64 * depth and packed[:4] == b"DPF1"
+            assert len(packed) == 32 + 64 * depth and packed[:4] == b"DPF2" and packed[4] == depth
+            assert packed[5:16] == bytes(11) and packed[16:32] == k[129 * 4:130 * 4].tobytes()
             assert np.array_equal(b200dpf.key_unpack(packed), k)
     k = torch.from_numpy(golden["keys_a"][5].copy())
     assert torch.equal(dpf_cpp.key_unpack(dpf_cpp.key_pack(k)), k)

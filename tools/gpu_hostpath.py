@@ -20,3 +20,5 @@ print("list (eval_gpu_list)   %.3f ms" % t(lambda: dpf_cpp.eval_gpu_list(lst,d.b
 print("list reference-style   %.3f ms" % t(lambda: dpf_cpp.eval_gpu(lst,d.buffers,n,3)))
 print("DPF.eval_gpu(list)     %.3f ms" % t(lambda: d.eval_gpu(lst)))
 print("torch.stack only       %.3f ms" % t(lambda: torch.stack(lst)))
+compact=d.pack_keys(lst)
+print("compact keys (%d B/key) %.3f ms" % (compact.shape[1], t(lambda: d.eval_gpu_compact(compact))))

@@ -81,14 +81,21 @@ __host__ __device__ constexpr Mix mix_of(int op)
          : Mix{2, 1, 0};
 }
 
-extern __shared__ uint32_t s_tab[];   // [256][32] words, 64 KiB-aligned window address not required here
+// 256 entries x 256 bytes (32 lanes x 4 bytes used), placed at a 64 KiB-aligned shared-window
+// address like the AES kernel's tables, so one PRMT (index byte -> byte 1 of base+4*lane) is the address
+extern __shared__ __align__(16) unsigned char s_raw[];
+#define TAB_SMEM (128 * 1024 + 16)
 
 template <int OP>
 __global__ void __launch_bounds__(512, 1) pipe_kernel(uint32_t *out, long long *cycles, int iters)
 {
-    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_tab[i] = i * 2654435761u;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t tab = (base + 65535u) & ~65535u;            /* 64 KiB-aligned window address inside the 128 KiB */
+    unsigned char *tabp = s_raw + (tab - base);
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x)
+        *reinterpret_cast<uint32_t *>(tabp + (i >> 5) * 256 + (i & 31) * 4) = i * 2654435761u;
     __syncthreads();
-    const uint32_t smem_lane = (uint32_t)__cvta_generic_to_shared(s_tab) + (threadIdx.x & 31) * 4;
+    const uint32_t smem_lane = tab + (threadIdx.x & 31) * 4;
     uint32_t x[CH];
 #pragma unroll
     for (int c = 0; c < CH; c++) x[c] = threadIdx.x * 2654435761u + c * 40503u + blockIdx.x;
@@ -218,13 +225,13 @@ template <int OP>
 static void run_pipe(const char *name)
 {
     auto k = pipe_kernel<OP>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TAB_SMEM);
     const int iters = 2000;
-    k<<<g_sms, 512, 32768>>>(g_out, g_cycles, 50);
+    k<<<g_sms, 512, TAB_SMEM>>>(g_out, g_cycles, 50);
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a);
-    k<<<g_sms, 512, 32768>>>(g_out, g_cycles, iters);
+    k<<<g_sms, 512, TAB_SMEM>>>(g_out, g_cycles, iters);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms = 0;
