@@ -20,7 +20,7 @@ PRF_NAMES = {0: "DUMMY", 1: "SALSA20", 2: "CHACHA20", 3: "AES128"}
 SYMBOLS = [
     "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_eval_cpu",
     "b200dpf_key_packed_size", "b200dpf_key_pack", "b200dpf_key_unpack", "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
-    "b200dpf_eval_packed", "b200dpf_ctx_set_option",
+    "b200dpf_eval_packed", "b200dpf_eval_gather", "b200dpf_ctx_set_option", "b200dpf_create_multi", "b200dpf_ctx_device_count", "b200dpf_ctx_axis", "b200dpf_ctx_read_timing",
     "b200dpf_host_staging", "b200dpf_eval_device", "b200dpf_eval_device_acc", "b200dpf_expand_device", "b200dpf_ctx_n", "b200dpf_ctx_entry_size",
     "b200dpf_ctx_device", "b200dpf_ctx_last_launches", "b200dpf_ctx_set_subtree_log2",
 ]
@@ -52,9 +52,15 @@ def load():
     L.b200dpf_key_n.restype = C.c_int64
     L.b200dpf_key_depth.argtypes = [_i32p]
     L.b200dpf_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.b200dpf_create_multi.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
+    L.b200dpf_ctx_device_count.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_axis.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_read_timing.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), C.c_int,
+                                          C.POINTER(C.c_int)]
     L.b200dpf_destroy.argtypes = [C.c_void_p]
     L.b200dpf_eval.argtypes = [C.c_void_p, _i32p, C.c_int64, C.c_int, _i32p]
     L.b200dpf_eval_packed.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int, _i32p]
+    L.b200dpf_eval_gather.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64, C.c_int, _i32p]
     L.b200dpf_ctx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.b200dpf_host_staging.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.POINTER(C.c_int32))]
     L.b200dpf_eval_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
@@ -144,6 +150,26 @@ class Context:
                                     device, shard_rank, shard_count), "b200dpf_create")
 
     @classmethod
+    def multi(cls, table, devices, axis=0):
+        """One table over several GPUs of this process; axis 0 auto, 1 entries, 2 keys."""
+        table = np.ascontiguousarray(table, np.int32)
+        self = cls.__new__(cls)
+        self.n, self.entry_size = table.shape
+        self.handle = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(lib().b200dpf_create_multi(C.byref(self.handle), table.ctypes.data_as(C.c_void_p), self.n, self.entry_size,
+                                          devs, len(devices), axis), "b200dpf_create_multi")
+        return self
+
+    @property
+    def device_count(self):
+        return lib().b200dpf_ctx_device_count(self.handle)
+
+    @property
+    def axis(self):
+        return lib().b200dpf_ctx_axis(self.handle)
+
+    @classmethod
     def from_device_ptr(cls, ptr, n, entry_size, device=0, shard_rank=0, shard_count=1):
         self = cls.__new__(cls)
         self.n, self.entry_size = n, entry_size
@@ -164,8 +190,23 @@ class Context:
         _check(lib().b200dpf_eval_packed(self.handle, bytes(packed), nkeys, prf, out), "b200dpf_eval_packed")
         return out
 
+    def eval_gather(self, key_list, prf):
+        """keys as a list of separate int32[524] arrays (the reference's calling convention)"""
+        arrs = [np.ascontiguousarray(k, np.int32) for k in key_list]
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        out = np.zeros((len(arrs), self.entry_size), np.int32)
+        _check(lib().b200dpf_eval_gather(self.handle, ptrs, len(arrs), prf, out), "b200dpf_eval_gather")
+        return out
+
     def set_option(self, name, value):
         _check(lib().b200dpf_ctx_set_option(self.handle, name.encode(), int(value)), "b200dpf_ctx_set_option")
+
+    def read_timing(self, max_blocks=1024):
+        """[blocks, 8] uint64 %globaltimer stamps of the last evaluation (option "timing" = 1)"""
+        buf = np.zeros((max_blocks, 8), np.uint64)
+        n = C.c_int()
+        _check(lib().b200dpf_ctx_read_timing(self.handle, buf, max_blocks, C.byref(n)), "b200dpf_ctx_read_timing")
+        return buf[:n.value]
 
     def eval_device(self, keys_ptr, nkeys, prf, out_ptr, stream=0, accumulate=False):
         fn = lib().b200dpf_eval_device_acc if accumulate else lib().b200dpf_eval_device

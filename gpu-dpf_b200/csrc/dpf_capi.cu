@@ -15,7 +15,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -69,8 +73,10 @@ struct DeviceGuard {
 }  // namespace
 
 struct SmemLayoutCache;   /* per (prf, nv, mode) launch layouts, filled on first use */
+struct MultiState;        /* b200dpf_create_multi: per-device sub-contexts + worker threads */
 
 struct b200dpf_ctx {
+    MultiState *multi = nullptr;   /* non-null: this context only fans out to multi->sub[] */
     SmemLayoutCache *layouts = nullptr;
     int device = 0;
     int64_t n = 0;
@@ -110,7 +116,11 @@ struct b200dpf_ctx {
         int subtree_log2 = 0;      /* B200DPF_S              0 = automatic                                  */
         int mac_tma = 1;           /* B200DPF_MAC_TMA        cp.async.bulk-staged MAC passes               */
         int one_launch = 1;        /* B200DPF_ONE_LAUNCH     whole evaluation as one cooperative launch    */
+        int balance_top = 1;       /* B200DPF_BALANCE_TOP    even per-block shares of the tree-top phase    */
+        int timing = 0;            /* B200DPF_TIMING         per-block phase time stamps (diagnostics)      */
     } knobs;
+    unsigned long long *d_timing = nullptr;   /* [timing_blocks][8] */
+    int timing_blocks = 0;
     int coop_ok = 0;               /* device supports cooperative launches                                 */
     uint32_t *d_top_counters = nullptr;   /* top-phase tickets: zero between launches (self re-arming)     */
     size_t top_counters_cap = 0;          /* bytes                                                          */
@@ -430,6 +440,22 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
         p.zero_b_words = n_main_counters;
         p.rearm = c->d_top_counters;
         p.rearm_words = (uint32_t)key_groups;
+        {
+            const uint64_t items = (uint64_t)key_groups * (uint64_t)(top.nsub >> spw_log2);
+            p.top_block_quota = K.balance_top ? (uint32_t)std::max<uint64_t>(1, (items + (uint64_t)L.grid - 1) / (uint64_t)L.grid)
+                                              : 0x7fffffffu;
+        }
+        if (K.timing) {
+            if (c->timing_blocks < L.grid) {
+                if (c->d_timing) cudaFree(c->d_timing);
+                c->d_timing = nullptr;
+                c->timing_blocks = 0;
+                CUDA_TRY(cudaMalloc(&c->d_timing, (size_t)L.grid * 8 * sizeof(unsigned long long)));
+                c->timing_blocks = L.grid;
+            }
+            CUDA_TRY(cudaMemsetAsync(c->d_timing, 0, (size_t)c->timing_blocks * 8 * sizeof(unsigned long long), stream));
+            p.timing = c->d_timing;
+        }
         p.grid_bar = c->d_gridbar;
         c->bar_epoch += (uint32_t)L.grid;
         p.grid_bar_target = c->bar_epoch;
@@ -575,7 +601,7 @@ int ensure_host_keys(b200dpf_ctx *c, int64_t nkeys)
 int check_eval_args(const b200dpf_ctx *c, const void *keys, int64_t nkeys, int prf, const void *out)
 {
     if (!c) return fail(B200DPF_EINVAL, "null context");
-    if (!c->d_table) return fail(B200DPF_ESTATE, "context has no table");
+    if (!c->d_table && !c->multi) return fail(B200DPF_ESTATE, "context has no table");
     if (!keys || !out) return fail(B200DPF_EINVAL, "null buffer");
     if (nkeys < 1 || nkeys > (int64_t)1 << 24) return fail(B200DPF_EINVAL, "nkeys=%lld out of range", (long long)nkeys);
     if (prf < B200DPF_PRF_DUMMY || prf > B200DPF_PRF_AES128) return fail(B200DPF_EINVAL, "unknown prf id %d", prf);
@@ -583,6 +609,14 @@ int check_eval_args(const b200dpf_ctx *c, const void *keys, int64_t nkeys, int p
 }
 
 }  // namespace
+
+/* multi-device contexts (defined at the end of this file) */
+static b200dpf_ctx *multi_first(b200dpf_ctx *root);
+static int multi_last_launches(const b200dpf_ctx *root);
+static int multi_set_option(b200dpf_ctx *root, const char *name, int value);
+static int multi_eval_host(b200dpf_ctx *root, const void *keys, size_t key_stride_bytes, const KeyLayout &kl, int64_t nkeys,
+                           int prf, int32_t *out);
+static void multi_destroy(b200dpf_ctx *root);
 
 extern "C" {
 
@@ -749,6 +783,8 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     c->knobs.subtree_log2 = env_int("B200DPF_S", c->knobs.subtree_log2);
     c->knobs.mac_tma = env_int("B200DPF_MAC_TMA", c->knobs.mac_tma);
     c->knobs.one_launch = env_int("B200DPF_ONE_LAUNCH", c->knobs.one_launch);
+    c->knobs.balance_top = env_int("B200DPF_BALANCE_TOP", c->knobs.balance_top);
+    c->knobs.timing = env_int("B200DPF_TIMING", c->knobs.timing);
     CTX_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
     CTX_TRY(upload_aes_table(host::aes_te0()));
 
@@ -831,6 +867,11 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
 int b200dpf_destroy(b200dpf_ctx *c)
 {
     if (!c) return B200DPF_OK;
+    if (c->multi) {
+        multi_destroy(c);
+        delete c;
+        return B200DPF_OK;
+    }
     DeviceGuard guard(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->d_table) cudaFree(c->d_table);
@@ -839,6 +880,7 @@ int b200dpf_destroy(b200dpf_ctx *c)
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_top_counters) cudaFree(c->d_top_counters);
     if (c->d_gridbar) cudaFree(c->d_gridbar);
+    if (c->d_timing) cudaFree(c->d_timing);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->d_frontier) cudaFree(c->d_frontier);
     if (c->d_leaf_cache) cudaFree(c->d_leaf_cache);
@@ -850,24 +892,18 @@ int b200dpf_destroy(b200dpf_ctx *c)
     return B200DPF_OK;
 }
 
-/* Host buffers in and out: keys (either layout) -> pinned staging if pageable -> H2D, the
- * evaluation, D2H, one stream synchronisation. */
-static int eval_host(b200dpf_ctx *c, const void *keys, size_t key_bytes, const KeyLayout &kl, int64_t nkeys, int prf,
-                     int32_t *out)
+/* device key / result buffers of the host-buffer entry points, grown on demand */
+static int ensure_device_io(b200dpf_ctx *c, size_t key_bytes, size_t out_elems)
 {
-    DeviceGuard guard(c->device);
-    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
-    int rc;
-    const size_t keys_cap_bytes = c->keys_cap * host::KEY_WORDS * sizeof(int32_t);
-    if (key_bytes > keys_cap_bytes) {
+    const size_t key_unit = host::KEY_WORDS * sizeof(int32_t);
+    if (key_bytes > c->keys_cap * key_unit) {
         if (c->d_keys) cudaFree(c->d_keys);
         c->d_keys = nullptr;
         c->keys_cap = 0;
-        const size_t cap_keys = (key_bytes + host::KEY_WORDS * sizeof(int32_t) - 1) / (host::KEY_WORDS * sizeof(int32_t));
-        CUDA_TRY(cudaMalloc(&c->d_keys, cap_keys * host::KEY_WORDS * sizeof(int32_t)));
+        const size_t cap_keys = (key_bytes + key_unit - 1) / key_unit;
+        CUDA_TRY(cudaMalloc(&c->d_keys, cap_keys * key_unit));
         c->keys_cap = cap_keys;
     }
-    const size_t out_elems = (size_t)nkeys * c->entry_size;
     if (out_elems > c->out_cap) {
         if (c->d_out) cudaFree(c->d_out);
         c->d_out = nullptr;
@@ -875,6 +911,32 @@ static int eval_host(b200dpf_ctx *c, const void *keys, size_t key_bytes, const K
         CUDA_TRY(cudaMalloc(&c->d_out, out_elems * sizeof(int32_t)));
         c->out_cap = out_elems;
     }
+    return B200DPF_OK;
+}
+
+static int ensure_host_out(b200dpf_ctx *c, size_t out_elems)
+{
+    if (out_elems <= c->h_out_cap) return B200DPF_OK;
+    if (c->h_out) cudaFreeHost(c->h_out);
+    c->h_out = nullptr;
+    c->h_out_cap = 0;
+    const size_t cap = std::max<size_t>(out_elems, 8192);
+    CUDA_TRY(cudaMallocHost(&c->h_out, cap * sizeof(int32_t)));
+    c->h_out_cap = cap;
+    return B200DPF_OK;
+}
+
+
+/* Host buffers in and out: keys (either layout) -> pinned staging if pageable -> H2D, the
+ * evaluation, D2H, one stream synchronisation. */
+static int eval_host(b200dpf_ctx *c, const void *keys, size_t key_bytes, const KeyLayout &kl, int64_t nkeys, int prf,
+                     int32_t *out)
+{
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    const size_t out_elems = (size_t)nkeys * c->entry_size;
+    int rc = ensure_device_io(c, key_bytes, out_elems);
+    if (rc) return rc;
     /* pageable host memory goes through the context's pinned staging so both copies are real
      * asynchronous DMA transfers; already-pinned buffers (ours or the caller's) are used as is */
     const void *src = keys;
@@ -886,14 +948,8 @@ static int eval_host(b200dpf_ctx *c, const void *keys, size_t key_bytes, const K
     }
     int32_t *dst = out;
     if (!is_pinned_host(out)) {
-        if (out_elems > c->h_out_cap) {
-            if (c->h_out) cudaFreeHost(c->h_out);
-            c->h_out = nullptr;
-            c->h_out_cap = 0;
-            const size_t cap = std::max<size_t>(out_elems, 8192);
-            CUDA_TRY(cudaMallocHost(&c->h_out, cap * sizeof(int32_t)));
-            c->h_out_cap = cap;
-        }
+        rc = ensure_host_out(c, out_elems);
+        if (rc) return rc;
         dst = c->h_out;
     }
     /* the previous evaluation may have run on a caller's stream: the staging copy below must not
@@ -916,7 +972,72 @@ int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, in
         if (host::key_n(keys + b * host::KEY_WORDS) != c->n)
             return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
                         (long long)host::key_n(keys + b * host::KEY_WORDS), (long long)c->n);
+    if (c->multi) return multi_eval_host(c, keys, host::KEY_WORDS * sizeof(int32_t), reference_layout(), nkeys, prf, out);
     return eval_host(c, keys, (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t), reference_layout(), nkeys, prf, out);
+}
+
+/* compact form of one key straight into `dst` (b200dpf_key_pack without the checks) */
+static inline void pack_compact(const int32_t *key, uint8_t *dst, int depth)
+{
+    const uint8_t *k = reinterpret_cast<const uint8_t *>(key);
+    std::memset(dst, 0, 16);
+    std::memcpy(dst, "DPF2", 4);
+    dst[4] = (uint8_t)depth;
+    std::memcpy(dst + 16, k + 16 * host::SLOT_ROOT, 16);
+    uint8_t *o = dst + 32;
+    const uint8_t *c1 = k + 16 * host::SLOT_CW1, *c2 = k + 16 * host::SLOT_CW2;
+    for (int L = 0; L < depth; L++, o += 64) {
+        std::memcpy(o, c1 + 32 * L, 32);
+        std::memcpy(o + 32, c2 + 32 * L, 32);
+    }
+}
+
+int b200dpf_eval_gather(b200dpf_ctx *c, const int32_t *const *keys, int64_t nkeys, int prf, int32_t *out)
+{
+    int rc = check_eval_args(c, keys, nkeys, prf, out);
+    if (rc) return rc;
+    for (int64_t b = 0; b < nkeys; b++)
+        if (!keys[b] || host::key_n(keys[b]) != c->n)
+            return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
+                        (long long)(keys[b] ? host::key_n(keys[b]) : -1), (long long)c->n);
+    b200dpf_ctx *c0 = c->multi ? multi_first(c) : c;
+    DeviceGuard guard(c0->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c0->device);
+    const size_t stride = b200dpf_key_packed_size(c->depth);
+    const size_t key_bytes = (size_t)nkeys * stride;
+    const size_t unit = host::KEY_WORDS * sizeof(int32_t);
+    rc = ensure_host_keys(c0, (int64_t)((key_bytes + unit - 1) / unit));
+    if (rc) return rc;
+    uint8_t *stage = reinterpret_cast<uint8_t *>(c0->h_keys);
+    if (c->multi) {
+        for (int64_t b = 0; b < nkeys; b++) pack_compact(keys[b], stage + (size_t)b * stride, c->depth);
+        return multi_eval_host(c, stage, stride, compact_layout(c->depth), nkeys, prf, out);
+    }
+    /* pack a chunk into pinned staging, start its DMA, pack the next: the copy engine works while
+     * the host gathers (the reference converts all 512 keys, then issues one blocking cudaMemcpy) */
+    const size_t out_elems = (size_t)nkeys * c->entry_size;
+    rc = ensure_device_io(c, key_bytes, out_elems);
+    if (rc) return rc;
+    if (c->has_last && c->last_stream != c->stream) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+    const int64_t chunk = 64;
+    for (int64_t b0 = 0; b0 < nkeys; b0 += chunk) {
+        const int64_t b1 = std::min(nkeys, b0 + chunk);
+        for (int64_t b = b0; b < b1; b++) pack_compact(keys[b], stage + (size_t)b * stride, c->depth);
+        CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(c->d_keys) + (size_t)b0 * stride, stage + (size_t)b0 * stride,
+                                 (size_t)(b1 - b0) * stride, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = run_pipeline(c, c->d_keys, compact_layout(c->depth), nkeys, prf, MODE_FUSED, c->d_out, c->stream);
+    if (rc) return rc;
+    int32_t *dst = out;
+    if (!is_pinned_host(out)) {
+        rc = ensure_host_out(c, out_elems);
+        if (rc) return rc;
+        dst = c->h_out;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dst, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (dst != out) std::memcpy(out, dst, out_elems * sizeof(int32_t));
+    return B200DPF_OK;
 }
 
 int b200dpf_eval_packed(b200dpf_ctx *c, const uint8_t *packed, int64_t nkeys, int prf, int32_t *out)
@@ -930,6 +1051,7 @@ int b200dpf_eval_packed(b200dpf_ctx *c, const uint8_t *packed, int64_t nkeys, in
             return fail(B200DPF_EINVAL, "packed key %lld: bad header or depth %d, table has depth %d (n=%lld)", (long long)b,
                         (int)k[4], c->depth, (long long)c->n);
     }
+    if (c->multi) return multi_eval_host(c, packed, stride, compact_layout(c->depth), nkeys, prf, out);
     return eval_host(c, packed, (size_t)nkeys * stride, compact_layout(c->depth), nkeys, prf, out);
 }
 
@@ -938,6 +1060,7 @@ int b200dpf_host_staging(b200dpf_ctx *c, int64_t nkeys, int32_t **keys_pinned)
     if (!c || !keys_pinned || nkeys < 1) return fail(B200DPF_EINVAL, "bad host_staging argument");
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    if (c->multi) c = multi_first(c);
     const int rc = ensure_host_keys(c, nkeys);
     if (rc) return rc;
     *keys_pinned = c->h_keys;
@@ -948,6 +1071,7 @@ int b200dpf_eval_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, int
 {
     int rc = check_eval_args(c, keys_dev, nkeys, prf, out_dev);
     if (rc) return rc;
+    if (c->multi) return fail(B200DPF_ESTATE, "multi-device contexts take host buffers (b200dpf_eval / b200dpf_eval_packed)");
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
     return run_eval(c, keys_dev, nkeys, prf, out_dev, reinterpret_cast<cudaStream_t>(cuda_stream));
@@ -957,6 +1081,7 @@ int b200dpf_eval_device_acc(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys,
 {
     int rc = check_eval_args(c, keys_dev, nkeys, prf, out_dev);
     if (rc) return rc;
+    if (c->multi) return fail(B200DPF_ESTATE, "multi-device contexts take host buffers (b200dpf_eval / b200dpf_eval_packed)");
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
     return run_pipeline(c, keys_dev, reference_layout(), nkeys, prf, MODE_FUSED, out_dev,
@@ -967,6 +1092,7 @@ int b200dpf_expand_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, i
 {
     int rc = check_eval_args(c, keys_dev, nkeys, prf, shares_dev);
     if (rc) return rc;
+    if (c->multi) return fail(B200DPF_ESTATE, "multi-device contexts take host buffers (b200dpf_eval / b200dpf_eval_packed)");
     if (c->shard_count != 1) return fail(B200DPF_ESTATE, "expand needs an unsharded context");
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
@@ -977,7 +1103,11 @@ int b200dpf_expand_device(b200dpf_ctx *c, const void *keys_dev, int64_t nkeys, i
 int64_t b200dpf_ctx_n(const b200dpf_ctx *c) { return c ? c->n : -1; }
 int b200dpf_ctx_entry_size(const b200dpf_ctx *c) { return c ? c->entry_size : -1; }
 int b200dpf_ctx_device(const b200dpf_ctx *c) { return c ? c->device : -1; }
-int b200dpf_ctx_last_launches(const b200dpf_ctx *c) { return c ? c->last_launches : -1; }
+int b200dpf_ctx_last_launches(const b200dpf_ctx *c)
+{
+    if (!c) return -1;
+    return c->multi ? multi_last_launches(c) : c->last_launches;
+}
 
 int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *c, int s)
 {
@@ -989,11 +1119,13 @@ int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *c, int s)
 int b200dpf_ctx_set_option(b200dpf_ctx *c, const char *name, int value)
 {
     if (!c || !name) return fail(B200DPF_EINVAL, "null argument");
+    if (c->multi) return multi_set_option(c, name, value);
     struct { const char *name; int *slot; int lo, hi; } opts[] = {
         {"leaf_cache", &c->knobs.leaf_cache, 0, 1},       {"leaf_cache_mb", &c->knobs.leaf_cache_mb, 1, 1 << 20},
         {"lane_split", &c->knobs.lane_split, 0, 1},       {"frontier", &c->knobs.frontier, 0, 1},
         {"frontier_mb", &c->knobs.frontier_mb, 1, 1 << 16}, {"subtree_log2", &c->knobs.subtree_log2, 0, 16},
         {"mac_tma", &c->knobs.mac_tma, 0, 1},             {"one_launch", &c->knobs.one_launch, 0, 1},
+        {"balance_top", &c->knobs.balance_top, 0, 1},     {"timing", &c->knobs.timing, 0, 1},
     };
     for (auto &o : opts)
         if (std::strcmp(o.name, name) == 0) {
@@ -1002,6 +1134,320 @@ int b200dpf_ctx_set_option(b200dpf_ctx *c, const char *name, int value)
             return B200DPF_OK;
         }
     return fail(B200DPF_EINVAL, "unknown option '%s'", name);
+}
+
+
+/* ------------------------------------------------------------------------------------------- */
+/* One process, several GPUs ("single process drives 1/2/4/8 GPUs"). */
+/* ------------------------------------------------------------------------------------------- */
+}  // extern "C"
+
+/*
+ * A multi-device context owns one ordinary context per GPU and one host worker thread per GPU
+ * beyond the first, so the per-device stream operations of an evaluation are issued in parallel
+ * (a single thread would serialise ~10 us of launch work per device).
+ *   axis ENTRIES: sub-context d is entry-range shard (d, ndev).  Every device receives every key,
+ *                 evaluates its subtree, and device 0 adds the partial results with a kernel that
+ *                 loads the peers' buffers over NVLink (host-side sum when peer access is absent).
+ *   axis KEYS:    every sub-context holds the whole table; the batch is cut into contiguous
+ *                 slices of whole key groups and nothing crosses GPUs.
+ */
+struct MultiState {
+    int ndev = 0;
+    int axis = B200DPF_AXIS_ENTRIES;
+    bool peer = false;
+    std::vector<b200dpf_ctx *> sub;
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv;
+    std::atomic<uint64_t> gen{0};
+    std::atomic<int> done{0};
+    std::atomic<bool> quit{false};
+    /* the job of the current generation */
+    const void *keys = nullptr;
+    size_t key_stride_bytes = 0;
+    KeyLayout kl{};
+    int64_t nkeys = 0;
+    int prf = 0;
+    int32_t *out = nullptr;
+    bool out_pinned = false;
+    std::vector<int64_t> k0, k1;      /* KEYS axis: slice of the batch per device */
+    std::vector<int> rc;
+    std::vector<std::string> err;
+};
+
+static inline void cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+}
+
+/* Everything device d does for the current job; runs on d's own host thread with d current. */
+static int multi_device_part(MultiState *M, int d)
+{
+    b200dpf_ctx *c = M->sub[(size_t)d];
+    int64_t b = 0, e = M->nkeys;
+    if (M->axis == B200DPF_AXIS_KEYS) {
+        b = M->k0[(size_t)d];
+        e = M->k1[(size_t)d];
+        if (e <= b) return B200DPF_OK;
+    }
+    const int64_t nk = e - b;
+    const size_t key_bytes = (size_t)nk * M->key_stride_bytes;
+    const size_t out_elems = (size_t)nk * c->entry_size;
+    int rc = ensure_device_io(c, key_bytes, out_elems);
+    if (rc) return rc;
+    if (c->has_last && c->last_stream != c->stream) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(c->d_keys, static_cast<const char *>(M->keys) + (size_t)b * M->key_stride_bytes, key_bytes,
+                             cudaMemcpyHostToDevice, c->stream));
+    rc = run_pipeline(c, c->d_keys, M->kl, nk, M->prf, MODE_FUSED, c->d_out, c->stream);
+    if (rc) return rc;
+    if (M->axis == B200DPF_AXIS_KEYS) {
+        int32_t *dst = M->out + (size_t)b * c->entry_size;
+        if (!M->out_pinned) {
+            rc = ensure_host_out(c, out_elems);
+            if (rc) return rc;
+            dst = c->h_out;
+        }
+        CUDA_TRY(cudaMemcpyAsync(dst, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (!M->out_pinned) std::memcpy(M->out + (size_t)b * c->entry_size, dst, out_elems * sizeof(int32_t));
+    } else if (!M->peer) {
+        rc = ensure_host_out(c, out_elems);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    /* ENTRIES + peer: run_pipeline recorded c->ev_done on c->stream; device 0 waits for it */
+    return B200DPF_OK;
+}
+
+static void multi_worker(MultiState *M, int d)
+{
+    cudaSetDevice(M->sub[(size_t)d]->device);
+    uint64_t seen = 0;
+    for (;;) {
+        int spins = 0;
+        while (M->gen.load(std::memory_order_acquire) == seen && !M->quit.load(std::memory_order_acquire)) {
+            if (++spins < 20000) {          /* ~1 ms of polling keeps back-to-back batches off the futex path */
+                cpu_relax();
+                continue;
+            }
+            std::unique_lock<std::mutex> lk(M->m);
+            M->cv.wait(lk, [&] { return M->gen.load(std::memory_order_acquire) != seen || M->quit.load(); });
+        }
+        if (M->quit.load(std::memory_order_acquire)) return;
+        seen = M->gen.load(std::memory_order_acquire);
+        const int rc = multi_device_part(M, d);
+        M->rc[(size_t)d] = rc;
+        if (rc) M->err[(size_t)d] = g_err;      /* g_err is thread-local: hand the text to the caller's thread */
+        M->done.fetch_add(1, std::memory_order_release);
+    }
+}
+
+static b200dpf_ctx *multi_first(b200dpf_ctx *root) { return root->multi->sub[0]; }
+
+static int multi_last_launches(const b200dpf_ctx *root)
+{
+    int total = 0;
+    for (const b200dpf_ctx *c : root->multi->sub) total += c->last_launches;
+    return total;
+}
+
+static int multi_set_option(b200dpf_ctx *root, const char *name, int value)
+{
+    for (b200dpf_ctx *c : root->multi->sub) {
+        const int rc = b200dpf_ctx_set_option(c, name, value);
+        if (rc) return rc;
+    }
+    return B200DPF_OK;
+}
+
+static void multi_destroy(b200dpf_ctx *root)
+{
+    MultiState *M = root->multi;
+    {
+        std::lock_guard<std::mutex> lk(M->m);
+        M->quit.store(true, std::memory_order_release);
+    }
+    M->cv.notify_all();
+    for (auto &t : M->workers) t.join();
+    for (b200dpf_ctx *c : M->sub) b200dpf_destroy(c);
+    delete M;
+    root->multi = nullptr;
+}
+
+static int multi_eval_host(b200dpf_ctx *root, const void *keys, size_t key_stride_bytes, const KeyLayout &kl, int64_t nkeys,
+                           int prf, int32_t *out)
+{
+    MultiState *M = root->multi;
+    b200dpf_ctx *c0 = M->sub[0];
+    DeviceGuard guard(c0->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c0->device);
+    /* every device DMA-reads the keys from the same host buffer: it has to be pinned */
+    const size_t key_bytes = (size_t)nkeys * key_stride_bytes;
+    const void *src = keys;
+    int rc;
+    if (!is_pinned_host(keys)) {
+        const size_t unit = host::KEY_WORDS * sizeof(int32_t);
+        rc = ensure_host_keys(c0, (int64_t)((key_bytes + unit - 1) / unit));
+        if (rc) return rc;
+        std::memcpy(c0->h_keys, keys, key_bytes);
+        src = c0->h_keys;
+    }
+    const size_t out_elems = (size_t)nkeys * root->entry_size;
+    M->keys = src;
+    M->key_stride_bytes = key_stride_bytes;
+    M->kl = kl;
+    M->nkeys = nkeys;
+    M->prf = prf;
+    M->out = out;
+    M->out_pinned = is_pinned_host(out);
+    if (M->axis == B200DPF_AXIS_KEYS) {
+        const int64_t groups = (nkeys + 31) / 32;
+        const int64_t per = ((groups + M->ndev - 1) / M->ndev) * 32;
+        for (int d = 0; d < M->ndev; d++) {
+            M->k0[(size_t)d] = std::min<int64_t>((int64_t)d * per, nkeys);
+            M->k1[(size_t)d] = std::min<int64_t>((int64_t)(d + 1) * per, nkeys);
+        }
+    }
+    for (int d = 0; d < M->ndev; d++) M->rc[(size_t)d] = B200DPF_OK;
+    M->done.store(0, std::memory_order_relaxed);
+    {
+        std::lock_guard<std::mutex> lk(M->m);
+        M->gen.fetch_add(1, std::memory_order_release);
+    }
+    M->cv.notify_all();
+    M->rc[0] = multi_device_part(M, 0);
+    if (M->rc[0]) M->err[0] = g_err;
+    while (M->done.load(std::memory_order_acquire) < M->ndev - 1) cpu_relax();
+    for (int d = 0; d < M->ndev; d++)
+        if (M->rc[(size_t)d]) return fail(M->rc[(size_t)d], "device %d: %s", M->sub[(size_t)d]->device, M->err[(size_t)d].c_str());
+    if (M->axis == B200DPF_AXIS_KEYS) return B200DPF_OK;     /* every device delivered its own rows */
+
+    if (M->peer) {
+        /* device 0: wait for every shard's kernel, then add the peers' partials over NVLink */
+        PeerParts parts;
+        parts.n = 0;
+        for (int d = 1; d < M->ndev; d++) {
+            CUDA_TRY(cudaStreamWaitEvent(c0->stream, M->sub[(size_t)d]->ev_done, 0));
+            parts.p[parts.n++] = reinterpret_cast<const uint32_t *>(M->sub[(size_t)d]->d_out);
+        }
+        CUDA_TRY(launch_sum_partials(reinterpret_cast<uint32_t *>(c0->d_out), parts, out_elems, c0->stream));
+        int32_t *dst = out;
+        if (!M->out_pinned) {
+            rc = ensure_host_out(c0, out_elems);
+            if (rc) return rc;
+            dst = c0->h_out;
+        }
+        CUDA_TRY(cudaMemcpyAsync(dst, c0->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c0->stream));
+        CUDA_TRY(cudaStreamSynchronize(c0->stream));
+        if (dst != out) std::memcpy(out, dst, out_elems * sizeof(int32_t));
+    } else {
+        /* no peer access between these devices: every shard already copied its partial to pinned
+         * host memory; wrapping 32-bit adds on the host */
+        uint32_t *o = reinterpret_cast<uint32_t *>(out);
+        std::memcpy(o, c0->h_out, out_elems * sizeof(int32_t));
+        for (int d = 1; d < M->ndev; d++) {
+            const uint32_t *part = reinterpret_cast<const uint32_t *>(M->sub[(size_t)d]->h_out);
+            for (size_t i = 0; i < out_elems; i++) o[i] += part[i];
+        }
+    }
+    return B200DPF_OK;
+}
+
+extern "C" {
+
+int b200dpf_create_multi(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry_size, const int *devices, int ndev,
+                         int axis)
+{
+    if (!out) return fail(B200DPF_EINVAL, "null ctx out pointer");
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > 16) return fail(B200DPF_EINVAL, "need 1..16 devices (got %d)", ndev);
+    if (axis != B200DPF_AXIS_AUTO && axis != B200DPF_AXIS_ENTRIES && axis != B200DPF_AXIS_KEYS)
+        return fail(B200DPF_EINVAL, "unknown axis %d", axis);
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) return fail(B200DPF_EINVAL, "device %d listed twice", devices[i]);
+    const bool pow2 = (ndev & (ndev - 1)) == 0;
+    if (axis == B200DPF_AXIS_AUTO)
+        axis = (pow2 && n > B200DPF_AUTO_KEYS_MAX_N && (int64_t)ndev <= n / 2) ? B200DPF_AXIS_ENTRIES : B200DPF_AXIS_KEYS;
+    if (axis == B200DPF_AXIS_ENTRIES && (!pow2 || (int64_t)ndev > n / 2))
+        return fail(B200DPF_EINVAL, "entry-range sharding needs a power-of-two device count <= n/2 (got %d)", ndev);
+
+    b200dpf_ctx *root = new (std::nothrow) b200dpf_ctx();
+    MultiState *M = new (std::nothrow) MultiState();
+    if (!root || !M) {
+        delete root;
+        delete M;
+        return fail(B200DPF_ENOMEM, "out of host memory");
+    }
+    root->multi = M;
+    root->n = n;
+    root->depth = ilog2(n);
+    root->entry_size = entry_size;
+    root->device = devices[0];
+    M->ndev = ndev;
+    M->axis = axis;
+    M->k0.assign((size_t)ndev, 0);
+    M->k1.assign((size_t)ndev, 0);
+    M->rc.assign((size_t)ndev, 0);
+    M->err.assign((size_t)ndev, std::string());
+    for (int d = 0; d < ndev; d++) {
+        b200dpf_ctx *c = nullptr;
+        const int rc = axis == B200DPF_AXIS_ENTRIES ? b200dpf_create(&c, table, n, entry_size, devices[d], d, ndev)
+                                                    : b200dpf_create(&c, table, n, entry_size, devices[d], 0, 1);
+        if (rc) {
+            for (b200dpf_ctx *s : M->sub) b200dpf_destroy(s);
+            delete M;
+            delete root;
+            return rc;     /* message already set by b200dpf_create */
+        }
+        M->sub.push_back(c);
+    }
+    /* device 0 reads the other shards' partial results in place: NVLink peer mappings */
+    M->peer = axis == B200DPF_AXIS_ENTRIES && ndev > 1;
+    if (M->peer) {
+        DeviceGuard guard(devices[0]);
+        for (int d = 1; d < ndev && M->peer; d++) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[0], devices[d]) != cudaSuccess || !can) M->peer = false;
+        }
+        for (int d = 1; d < ndev && M->peer; d++) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[d], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) M->peer = false;
+        }
+        cudaGetLastError();
+    }
+    for (int d = 1; d < ndev; d++) M->workers.emplace_back(multi_worker, M, d);
+    *out = root;
+    return B200DPF_OK;
+}
+
+int b200dpf_ctx_read_timing(b200dpf_ctx *c, uint64_t *stamps, int max_blocks, int *nblocks)
+{
+    if (!c || !stamps || !nblocks) return fail(B200DPF_EINVAL, "null argument");
+    if (c->multi) c = multi_first(c);
+    *nblocks = 0;
+    if (!c->d_timing) return B200DPF_OK;
+    DeviceGuard guard(c->device);
+    const int nb = std::min(max_blocks, c->timing_blocks);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(stamps, c->d_timing, (size_t)nb * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    *nblocks = nb;
+    return B200DPF_OK;
+}
+
+int b200dpf_ctx_device_count(const b200dpf_ctx *c) { return !c ? -1 : (c->multi ? c->multi->ndev : 1); }
+
+int b200dpf_ctx_axis(const b200dpf_ctx *c)
+{
+    if (!c) return -1;
+    if (c->multi) return c->multi->axis;
+    return c->shard_count > 1 ? B200DPF_AXIS_ENTRIES : B200DPF_AXIS_AUTO;
 }
 
 }  // extern "C"

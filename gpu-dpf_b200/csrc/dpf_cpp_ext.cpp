@@ -16,7 +16,11 @@
  *     expand_gpu, version; attribute NATIVE_SHAPES = 1 advertises them.
  */
 #include <torch/extension.h>
+#include <torch/csrc/autograd/python_variable.h>
 
+#include <ATen/detail/CUDAHooksInterface.h>
+
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -129,8 +133,58 @@ std::vector<void *> eval_init_sharded(const at::Tensor &table, int device, int s
     return {static_cast<void *>(ctx)};
 }
 
-/* dpf_wrapper.cu:93-132 */
-std::vector<void *> eval_init(const at::Tensor &table) { return eval_init_sharded(table, 0, 0, 1); }
+/* one table on several GPUs of this process (b200dpf_create_multi); axis: 0 auto, 1 entries, 2 keys */
+std::vector<void *> eval_init_multi(const at::Tensor &table, const std::vector<int> &devices, int axis)
+{
+    TORCH_CHECK(table.dim() == 2, "eval_init: table must be [num_entries, entry_size]");
+    TORCH_CHECK(!devices.empty(), "eval_init_multi: empty device list");
+    at::Tensor t = table.to(at::kInt).contiguous().cpu();
+    b200dpf_ctx *ctx = nullptr;
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_create_multi(&ctx, t.data_ptr<int32_t>(), t.size(0), (int)t.size(1), devices.data(), (int)devices.size(),
+                                   axis),
+              "eval_init");
+    }
+    return {static_cast<void *>(ctx)};
+}
+
+/* "all" / "" -> every visible device; "0,2,3" -> that list */
+std::vector<int> parse_devices(const std::string &spec)
+{
+    std::vector<int> devs;
+    if (spec.empty() || spec == "all") {
+        const int n = (int)at::detail::getCUDAHooks().deviceCount();
+        for (int i = 0; i < n; i++) devs.push_back(i);
+        return devs;
+    }
+    size_t pos = 0;
+    while (pos < spec.size()) {
+        size_t next = spec.find(',', pos);
+        if (next == std::string::npos) next = spec.size();
+        devs.push_back(std::stoi(spec.substr(pos, next - pos)));
+        pos = next + 1;
+    }
+    return devs;
+}
+
+/* dpf_wrapper.cu:93-132.  The reference's eval_init has no device argument (device 0, implicitly);
+ * B200DPF_DEVICES=all|0,1,.. in the environment makes this same call spread the table over several
+ * GPUs, so the reference's unmodified dpf.py / benchmark.py scale without a launcher. */
+std::vector<void *> eval_init(const at::Tensor &table)
+{
+    const char *env = std::getenv("B200DPF_DEVICES");
+    if (env && *env) {
+        std::vector<int> devs = parse_devices(env);
+        if (devs.size() > 1) {
+            const char *ax = std::getenv("B200DPF_AXIS");
+            const std::string a = ax ? ax : "auto";
+            return eval_init_multi(table, devs, a == "entries" ? B200DPF_AXIS_ENTRIES : (a == "keys" ? B200DPF_AXIS_KEYS : B200DPF_AXIS_AUTO));
+        }
+        if (devs.size() == 1) return eval_init_sharded(table, devs[0], 0, 1);
+    }
+    return eval_init_sharded(table, 0, 0, 1);
+}
 
 /* dpf_wrapper.cu:86-91 */
 void eval_free(const std::vector<void *> &buffers)
@@ -173,47 +227,65 @@ at::Tensor eval_gpu_compact(const at::Tensor &packed, int64_t nkeys, const std::
     return result;
 }
 
-/* keys as a Python list of int32[524] CPU tensors, any length -> int32[len, E] CPU tensor
- * (packing done here, not with torch.stack in Python) */
-at::Tensor eval_gpu_list(const std::vector<at::Tensor> &keys, const std::vector<void *> &buffers, int prf)
+/* Data pointers of a Python list of int32[524] CPU key tensors, without building a
+ * std::vector<at::Tensor> (512 reference-count round trips per call): the list is walked with the
+ * CPython API and each element unwrapped in place.  `unique` = length with trailing repeats of the
+ * SAME tensor object dropped (the reference's dpf.py pads short batches that way, dpf.py:126). */
+std::vector<const int32_t *> key_pointers(const py::object &keys_in, int64_t *unique)
+{
+    /* any sequence is accepted; a list (what dpf.py passes) is walked in place */
+    const py::list keys = py::isinstance<py::list>(keys_in) ? py::reinterpret_borrow<py::list>(keys_in) : py::list(keys_in);
+    const int64_t total = (int64_t)PyList_GET_SIZE(keys.ptr());
+    std::vector<const int32_t *> ptrs((size_t)total);
+    PyObject *prev = nullptr;
+    int64_t uniq = 0;
+    for (int64_t i = 0; i < total; i++) {
+        PyObject *o = PyList_GET_ITEM(keys.ptr(), i);
+        if (o == prev) {                         /* same object as its predecessor: same pointer */
+            ptrs[(size_t)i] = ptrs[(size_t)i - 1];
+            continue;
+        }
+        TORCH_CHECK(THPVariable_Check(o), "dpf_cpp: keys must be torch tensors");
+        ptrs[(size_t)i] = key_ptr(THPVariable_Unpack(o));
+        prev = o;
+        uniq = i + 1;
+    }
+    if (unique) *unique = uniq;
+    return ptrs;
+}
+
+/* keys as a Python list of int32[524] CPU tensors, any length -> int32[len, E] CPU tensor */
+at::Tensor eval_gpu_list(const py::object &keys, const std::vector<void *> &buffers, int prf)
 {
     b200dpf_ctx *ctx = ctx_of(buffers);
-    const int64_t total = (int64_t)keys.size();
-    const int64_t esz = b200dpf_ctx_entry_size(ctx);
-    at::Tensor result = torch::empty({total, esz}, at::kInt);
+    int64_t unique = 0;
+    std::vector<const int32_t *> ptrs = key_pointers(keys, &unique);
+    const int64_t total = (int64_t)ptrs.size();
+    at::Tensor result = torch::empty({total, (int64_t)b200dpf_ctx_entry_size(ctx)}, at::kInt);
     if (total == 0) return result;
-    int32_t *packed = nullptr;   /* the context's pinned staging: packed once, DMA'd from there */
-    check(b200dpf_host_staging(ctx, total, &packed), "eval_gpu");
-    for (int64_t i = 0; i < total; i++)
-        std::memcpy(packed + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
     {
         py::gil_scoped_release nogil;
-        check(b200dpf_eval(ctx, packed, total, prf, result.data_ptr<int32_t>()), "eval_gpu");
+        check(b200dpf_eval_gather(ctx, ptrs.data(), total, prf, result.data_ptr<int32_t>()), "eval_gpu");
     }
     return result;
 }
 
-/* dpf_wrapper.cu:134-186.  The reference's dpf.py pads short batches by
- * repeating the LAST key object (dpf.py:126); trailing repeats of one tensor
- * are evaluated once and their rows replicated. */
-at::Tensor eval_gpu(const std::vector<at::Tensor> &keys, const std::vector<void *> &buffers, int64_t n, int prf)
+/* dpf_wrapper.cu:134-186.  The reference's dpf.py pads short batches by repeating the LAST key
+ * object (dpf.py:126); trailing repeats of one tensor are evaluated once and their rows replicated. */
+at::Tensor eval_gpu(const py::object &keys, const std::vector<void *> &buffers, int64_t n, int prf)
 {
     b200dpf_ctx *ctx = ctx_of(buffers);
-    TORCH_CHECK(!keys.empty(), "eval_gpu: no keys");
     TORCH_CHECK(n == b200dpf_ctx_n(ctx), "eval_gpu: n does not match the initialised table");
-    const int64_t total = (int64_t)keys.size();
-    int64_t unique = total;
-    while (unique > 1 && keys[(size_t)unique - 1].unsafeGetTensorImpl() == keys[(size_t)unique - 2].unsafeGetTensorImpl()) unique--;
+    int64_t unique = 0;
+    std::vector<const int32_t *> ptrs = key_pointers(keys, &unique);
+    TORCH_CHECK(!ptrs.empty(), "eval_gpu: no keys");
+    const int64_t total = (int64_t)ptrs.size();
     const int64_t esz = b200dpf_ctx_entry_size(ctx);
-    int32_t *packed = nullptr;
-    check(b200dpf_host_staging(ctx, unique, &packed), "eval_gpu");
-    for (int64_t i = 0; i < unique; i++)
-        std::memcpy(packed + (size_t)i * kKeyWords, key_ptr(keys[(size_t)i]), sizeof(int32_t) * kKeyWords);
     at::Tensor result = torch::empty({total, esz}, at::kInt);
     int32_t *r = result.data_ptr<int32_t>();
     {
         py::gil_scoped_release nogil;
-        check(b200dpf_eval(ctx, packed, unique, prf, r), "eval_gpu");
+        check(b200dpf_eval_gather(ctx, ptrs.data(), unique, prf, r), "eval_gpu");
     }
     for (int64_t i = unique; i < total; i++) std::memcpy(r + i * esz, r + (unique - 1) * esz, sizeof(int32_t) * (size_t)esz);
     return result;
@@ -277,6 +349,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           py::arg("prf"), py::arg("nthreads") = 0);
     m.def("eval_init_sharded", &eval_init_sharded, "eval_init for one entry-range shard", py::arg("table"),
           py::arg("device"), py::arg("shard_rank"), py::arg("shard_count"));
+    m.def("eval_init_multi", &eval_init_multi, "eval_init over several GPUs of this process", py::arg("table"),
+          py::arg("devices"), py::arg("axis") = 0);
+    m.def("parse_devices", &parse_devices, "'all' or '0,1,2' -> device list");
+    m.def("device_count", [](const std::vector<void *> &b) { return b200dpf_ctx_device_count(ctx_of(b)); });
+    m.def("axis", [](const std::vector<void *> &b) { return b200dpf_ctx_axis(ctx_of(b)); });
     m.def("eval_gpu_packed", &eval_gpu_packed, "eval_gpu with keys as one [B,524] tensor");
     m.def("eval_gpu_list", &eval_gpu_list, "eval_gpu with keys as a list of any length");
     m.def("eval_gpu_device", &eval_gpu_device, "device-resident asynchronous evaluation", py::arg("keys_ptr"),

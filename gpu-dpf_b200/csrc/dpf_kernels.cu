@@ -54,6 +54,7 @@
  */
 #include "dpf_kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 
 #include "dpf_core.cuh"
@@ -220,9 +221,17 @@ __device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t target)
 /* One traversal phase of a launch: every block walks the key groups (starting at its own offset so
  * blocks spread over groups), loads a group's correction words into shared memory when the group
  * still has tickets, and its warps draw work items until the group runs dry. */
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+/* `quota`: tickets this WARP may draw in this call over all key groups (0xffffffff = no limit). */
 template <int PRF, int NV, int THREADS, int MODE>
 __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams &ph,
-                                          const typename TablePolicy<PRF>::type &ta)
+                                          const typename TablePolicy<PRF>::type &ta, uint32_t quota = 0xffffffffu)
 {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -250,9 +259,11 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
     env.row_stride_v = p.row_stride_v;
     env.depth = p.depth;
 
+    uint32_t taken = 0;
     for (int j = 0; j < p.key_groups; j++) {
         const int kg = (int)((blockIdx.x + (unsigned)j) % (unsigned)p.key_groups);
 
+        if (quota != 0xffffffffu && __syncthreads_and(taken >= quota)) break;   /* the block's share is done */
         if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(ph.counters + kg) < ntickets) ? 1 : 0;
         __syncthreads();
         const bool has_work = (*flag_s != 0);
@@ -294,10 +305,12 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
         const Seed root = make_seed(rv.x, rv.y, rv.z, rv.w);
 
         for (;;) {
+            if (taken >= quota) break;
             uint32_t t = 0;
             if (lane == 0) t = atomicAdd(ph.counters + kg, 1u);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= ntickets) break;
+            taken++;
             const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
             if (ph.frontier_in != nullptr) {
@@ -343,6 +356,8 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
 {
     constexpr int THREADS = KernelShape<PRF, NV>::THREADS;
     const int tid = threadIdx.x;
+    unsigned long long *stamp = (p.timing != nullptr && tid == 0) ? p.timing + (size_t)blockIdx.x * 8 : nullptr;
+    if (stamp) stamp[0] = global_ns();
 
     typename TablePolicy<PRF>::type ta;
     if constexpr (PRF == PRF_AES128) {
@@ -367,13 +382,24 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
             const uint64_t gtid = (uint64_t)blockIdx.x * THREADS + tid, gthreads = (uint64_t)gridDim.x * THREADS;
             for (uint64_t i = gtid; i < p.zero_a_words; i += gthreads) p.zero_a[i] = 0u;
             for (uint64_t i = gtid; i < p.zero_b_words; i += gthreads) p.zero_b[i] = 0u;
-            if (p.top.nsub != 0) run_phase<PRF, 4, THREADS, MODE_FRONTIER>(p, p.top, ta);
+            if (stamp) stamp[1] = global_ns();
+            if (p.top.nsub != 0) {
+                /* round 1: every block takes its even share (warp w: quota/nwarps, +1 for the first
+                 * quota%nwarps warps); round 2: whatever is left, first come first served */
+                constexpr uint32_t NW = THREADS / 32;
+                const uint32_t w = (uint32_t)tid >> 5;
+                run_phase<PRF, 4, THREADS, MODE_FRONTIER>(p, p.top, ta, p.top_block_quota / NW + (w < p.top_block_quota % NW ? 1u : 0u));
+                run_phase<PRF, 4, THREADS, MODE_FRONTIER>(p, p.top, ta);
+            }
+            if (stamp) stamp[2] = global_ns();
             grid_barrier(p.grid_bar, p.grid_bar_target);
+            if (stamp) stamp[3] = global_ns();
             if (blockIdx.x == 0)   /* nobody draws top-phase tickets any more: re-arm them for the next launch */
                 for (uint32_t i = tid; i < p.rearm_words; i += THREADS) p.rearm[i] = 0u;
         }
     }
     run_phase<PRF, NV, THREADS, MODE>(p, p.main, ta);
+    if (stamp) stamp[4] = global_ns();
 }
 
 /* MAC-only pass for wide entries: leaves come from the cache written by the first fused
@@ -575,6 +601,28 @@ __global__ void __launch_bounds__(MacTmaShape<NV>::THREADS, 1) dpf_mac_tma_kerne
     }
 }
 
+__global__ void __launch_bounds__(256) sum_partials_kernel(uint32_t *__restrict__ dst, const PeerParts parts, size_t words)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    if ((words & 3u) == 0) {   /* results are [B][E] int32 from cudaMalloc: 16-byte aligned whenever the count allows */
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+        for (size_t i = tid; i < words / 4; i += nthr) {
+            uint4 a = d4[i];
+            for (int k = 0; k < parts.n; k++) {
+                const uint4 b = __ldcg(reinterpret_cast<const uint4 *>(parts.p[k]) + i);   /* peer memory over NVLink */
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            d4[i] = a;
+        }
+    } else {
+        for (size_t i = tid; i < words; i += nthr) {
+            uint32_t a = dst[i];
+            for (int k = 0; k < parts.n; k++) a += __ldcg(parts.p[k] + i);
+            dst[i] = a;
+        }
+    }
+}
+
 __global__ void probe_smem_kernel(uint32_t *out)
 {
     if (threadIdx.x == 0) *out = (uint32_t)__cvta_generic_to_shared(g_dyn_smem);
@@ -733,6 +781,14 @@ cudaError_t launch_mac(int nv, const MacParams &p, int grid, cudaStream_t stream
     else if (nv == 8) dpf_mac_kernel<8><<<grid, 256, 0, stream>>>(p);
     else if (nv == 16) dpf_mac_kernel<16><<<grid, 256, 0, stream>>>(p);
     else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_partials(uint32_t *dst, const PeerParts &parts, size_t words, cudaStream_t stream)
+{
+    if (parts.n <= 0 || words == 0) return cudaSuccess;
+    int grid = (int)std::min<size_t>((words / 4 + 255) / 256 + 1, 148 * 4);
+    sum_partials_kernel<<<grid, 256, 0, stream>>>(dst, parts, words);
     return cudaGetLastError();
 }
 

@@ -65,6 +65,12 @@ struct EvalParams {
     uint32_t rearm_words;
     uint32_t *grid_bar;       /* monotonic arrival counter of the context               */
     uint32_t grid_bar_target; /* value it reaches when every block of this launch arrived */
+    uint32_t top_block_quota; /* tickets one block may draw in the first, balanced round of `top`
+                                 (ceil(items / blocks)): the top of the tree is little work, and
+                                 first-come-first-served would pile it onto the blocks that start
+                                 first; a second, unrestricted round mops up anything left        */
+    unsigned long long *timing; /* optional [blocks][8] %globaltimer stamps: start, tables built,
+                                 top done, barrier passed, end                                    */
     uint4 *frontier_out;      /* frontier written by `top` (or by the stand-alone kernel) */
     uint32_t nfront;          /* frontier nodes per key (this shard)                    */
     /* wide entries: the first pass also stores every leaf's low word, [key group][leaf
@@ -124,6 +130,15 @@ cudaError_t launch_mac(int nv, const MacParams &p, int grid, cudaStream_t stream
 /* Same pass (64 columns) with the operands staged into shared memory by cp.async.bulk
  * (TMA) under mbarriers: 8 key groups per block share every staged row slice. */
 cudaError_t launch_mac_tma(const MacParams &p, int grid, cudaStream_t stream);
+
+/* Cross-GPU reduction of entry-range partials inside one process: dst[i] += sum_k parts.p[k][i]
+ * (mod 2^32).  The kernel runs on the GPU that owns dst and LOADS the other GPUs' partial results
+ * through NVLink peer mappings -- no staging copies, no collective library. */
+struct PeerParts {
+    const uint32_t *p[15];
+    int n;
+};
+cudaError_t launch_sum_partials(uint32_t *dst, const PeerParts &parts, size_t words, cudaStream_t stream);
 
 /* Maximum dynamic shared memory the evaluation kernel may be given. */
 cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes);

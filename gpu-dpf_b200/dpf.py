@@ -56,7 +56,19 @@ class DPF(object):
         dpf_cpp.PRF_AES128: "AES128",
     }
 
-    def __init__(self, prf=None, device=0, shard=(0, 1), allow_non_pow2=False):
+    def __init__(self, prf=None, device=0, shard=(0, 1), allow_non_pow2=False, devices=None, axis="auto"):
+        # devices: None (one GPU: `device`), "all", or a list of device ids -- one process drives them all
+        # (b200dpf_create_multi); axis "auto" | "entries" | "keys".  B200DPF_DEVICES / B200DPF_AXIS in the
+        # environment set the defaults, so an unchanged `dpf.DPF()` caller (benchmark.py) can scale too.
+        if devices is None and os.environ.get("B200DPF_DEVICES"):
+            devices = os.environ["B200DPF_DEVICES"]
+            axis = os.environ.get("B200DPF_AXIS", axis)
+        if isinstance(devices, str):
+            devices = dpf_cpp.parse_devices(devices)
+        self.devices = list(devices) if devices is not None and len(devices) > 1 else None
+        if devices is not None and len(devices) == 1:
+            device = devices[0]
+        self.axis = axis
         # allow_non_pow2: tables / domains whose size is not a power of two are padded with zero
         # rows up to the next one (a reference TODO, dpf.py:21; off by default so the reference's
         # "must be a power of two" errors stay as they are)
@@ -123,7 +135,10 @@ class DPF(object):
         self.table = table
         self.table_num_entries = table.shape[0]
         self.table_effective_entry_size = table.shape[1]
-        self.buffers = dpf_cpp.eval_init_sharded(table, self.device, self.shard[0], self.shard[1])
+        if self.devices:
+            self.buffers = dpf_cpp.eval_init_multi(table, self.devices, {"auto": 0, "entries": 1, "keys": 2}[self.axis])
+        else:
+            self.buffers = dpf_cpp.eval_init_sharded(table, self.device, self.shard[0], self.shard[1])
 
     def eval_gpu(self, keys):
         """Evaluate a batch on the GPU (dpf.py:115-131): int32 [len(keys), entry_size] on the CPU.

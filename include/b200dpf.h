@@ -155,6 +155,30 @@ int b200dpf_key_depth(const int32_t *key);
 int b200dpf_create(b200dpf_ctx **ctx, const int32_t *table, int64_t n, int entry_size,
                    int device, int shard_rank, int shard_count);
 
+/*
+ * One table on SEVERAL GPUs of this process (the reference is
+ * single-GPU: device 0 implicitly, dpf_wrapper.cu:114-129).  The returned context is used with
+ * b200dpf_eval / b200dpf_eval_packed / b200dpf_destroy exactly like a single-device one, so a
+ * caller of the reference API scales without a process launcher.
+ *   axis B200DPF_AXIS_ENTRIES  device d owns entry-range shard (d, ndev) (ndev a power of two):
+ *                              every device evaluates every key over its subtree and device
+ *                              devices[0] adds the [nkeys][entry_size] partials with a kernel that
+ *                              loads the peers' buffers over NVLink.
+ *        B200DPF_AXIS_KEYS     every device holds the whole table and evaluates a contiguous
+ *                              slice of the batch; nothing crosses GPUs.
+ *        B200DPF_AXIS_AUTO     KEYS for n <= B200DPF_AUTO_KEYS_MAX_N (a shard of a small table
+ *                              cannot keep a GPU busy), else ENTRIES.
+ * One host thread per extra device issues that device's copies and launches.
+ */
+enum { B200DPF_AXIS_AUTO = 0, B200DPF_AXIS_ENTRIES = 1, B200DPF_AXIS_KEYS = 2 };
+#define B200DPF_AUTO_KEYS_MAX_N (1 << 18)
+int b200dpf_create_multi(b200dpf_ctx **ctx, const int32_t *table, int64_t n, int entry_size,
+                         const int *devices, int ndev, int axis);
+
+/* Devices behind a context (1 unless it came from b200dpf_create_multi) and its axis. */
+int b200dpf_ctx_device_count(const b200dpf_ctx *ctx);
+int b200dpf_ctx_axis(const b200dpf_ctx *ctx);
+
 /* Replaces: dpf_cpp.eval_free -> eval_free()               dpf_wrapper.cu:86-91. */
 int b200dpf_destroy(b200dpf_ctx *ctx);
 
@@ -167,6 +191,15 @@ int b200dpf_destroy(b200dpf_ctx *ctx);
  * reference requires exactly 512).
  */
 int b200dpf_eval(b200dpf_ctx *ctx, const int32_t *keys, int64_t nkeys, int prf, int32_t *out);
+
+/*
+ * Same evaluation with the batch given as nkeys POINTERS to int32[524] keys -- the shape the
+ * reference's eval_gpu receives (a vector of 512 key tensors, dpf_wrapper.cu:134-146).  Replaces
+ * its per-key marshalling loop + blocking upload (dpf_wrapper.cu:137-150): the live parts of each
+ * key are gathered into pinned staging in the compact layout and uploaded chunk by chunk while the
+ * host gathers the next chunk.
+ */
+int b200dpf_eval_gather(b200dpf_ctx *ctx, const int32_t *const *keys, int64_t nkeys, int prf, int32_t *out);
 
 /*
  * Same evaluation with keys in the compact wire form (b200dpf_key_pack): `packed` holds nkeys
@@ -241,9 +274,18 @@ int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *ctx, int s);
  *   "leaf_cache"    (B200DPF_LEAF_CACHE, 1)     entry_size > 32: expand once, MAC-only passes
  *   "leaf_cache_mb" (B200DPF_LEAF_CACHE_MB, 16384)  cap; larger batches run in chunks that fit
  *   "mac_tma"       (B200DPF_MAC_TMA, 1)        cp.async.bulk-staged MAC passes
+ *   "balance_top"   (B200DPF_BALANCE_TOP, 1)    even per-block shares of the tree-top phase
+ *   "timing"        (B200DPF_TIMING, 0)         record per-block phase time stamps (diagnostics)
  * Results never depend on them.
  */
 int b200dpf_ctx_set_option(b200dpf_ctx *ctx, const char *name, int value);
+
+/*
+ * Diagnostics ("timing" option): %globaltimer nanosecond stamps of the last single-launch
+ * evaluation, 8 uint64 per block: [0] kernel start, [1] tables + clears done, [2] tree-top
+ * phase done, [3] grid barrier passed, [4] main phase done, rest zero.  Synchronises the device.
+ */
+int b200dpf_ctx_read_timing(b200dpf_ctx *ctx, uint64_t *stamps, int max_blocks, int *nblocks);
 
 #ifdef __cplusplus
 }
