@@ -21,6 +21,7 @@ SYMBOLS = [
     "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_eval_cpu",
     "b200dpf_key_packed_size", "b200dpf_key_pack", "b200dpf_key_unpack", "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
     "b200dpf_eval_packed", "b200dpf_eval_gather", "b200dpf_ctx_set_option", "b200dpf_create_multi", "b200dpf_ctx_device_count", "b200dpf_ctx_axis", "b200dpf_ctx_read_timing",
+    "b200dpf_group_create", "b200dpf_group_eval", "b200dpf_group_bins",
     "b200dpf_host_staging", "b200dpf_eval_device", "b200dpf_eval_device_acc", "b200dpf_expand_device", "b200dpf_ctx_n", "b200dpf_ctx_entry_size",
     "b200dpf_ctx_device", "b200dpf_ctx_last_launches", "b200dpf_ctx_set_subtree_log2",
 ]
@@ -55,6 +56,9 @@ def load():
     L.b200dpf_create_multi.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
     L.b200dpf_ctx_device_count.argtypes = [C.c_void_p]
     L.b200dpf_ctx_axis.argtypes = [C.c_void_p]
+    L.b200dpf_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64p, C.c_int, C.c_int, C.c_int]
+    L.b200dpf_group_eval.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int64, C.c_int, _i32p]
+    L.b200dpf_group_bins.argtypes = [C.c_void_p]
     L.b200dpf_ctx_read_timing.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), C.c_int,
                                           C.POINTER(C.c_int)]
     L.b200dpf_destroy.argtypes = [C.c_void_p]
@@ -234,3 +238,31 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class GroupContext(Context):
+    """Many tables ("bins") of one entry size behind one context: the batch-PIR front end
+    (b200dpf_group_create / b200dpf_group_eval)."""
+
+    def __init__(self, tables, device=0):
+        self.tables = [np.ascontiguousarray(t, np.int32) for t in tables]
+        assert all(t.ndim == 2 and t.shape[1] == self.tables[0].shape[1] for t in self.tables)
+        self.entry_size = self.tables[0].shape[1]
+        self.n = max(t.shape[0] for t in self.tables)
+        sizes = np.array([t.shape[0] for t in self.tables], np.int64)
+        ptrs = (C.c_void_p * len(self.tables))(*[t.ctypes.data for t in self.tables])
+        self.handle = C.c_void_p()
+        _check(lib().b200dpf_group_create(C.byref(self.handle), ptrs, sizes, len(self.tables), self.entry_size, device),
+               "b200dpf_group_create")
+
+    @property
+    def nbins(self):
+        return lib().b200dpf_group_bins(self.handle)
+
+    def eval(self, keys, bins, prf):
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, KEY_WORDS)
+        bins = np.ascontiguousarray(bins, np.int32)
+        assert bins.shape == (keys.shape[0],)
+        out = np.zeros((keys.shape[0], self.entry_size), np.int32)
+        _check(lib().b200dpf_group_eval(self.handle, keys, bins, keys.shape[0], prf, out), "b200dpf_group_eval")
+        return out

@@ -75,8 +75,20 @@ struct DeviceGuard {
 struct SmemLayoutCache;   /* per (prf, nv, mode) launch layouts, filled on first use */
 struct MultiState;        /* b200dpf_create_multi: per-device sub-contexts + worker threads */
 
+struct GroupBins {            /* b200dpf_group_create: many tables ("bins") behind one context */
+    std::vector<int64_t> n;
+    std::vector<int> depth;
+    std::vector<uint64_t> row_off;     /* first row of the bin in d_table */
+    GroupDesc *d_descs = nullptr;
+    size_t descs_cap = 0;              /* descriptors */
+    GroupDesc *h_descs = nullptr;      /* pinned */
+    size_t h_descs_cap = 0;
+    std::vector<int64_t> perm;         /* sorted position -> caller's index, of the last evaluation */
+};
+
 struct b200dpf_ctx {
     MultiState *multi = nullptr;   /* non-null: this context only fans out to multi->sub[] */
+    GroupBins *bins = nullptr;     /* non-null: grouped (batch-PIR) context, use b200dpf_group_eval */
     SmemLayoutCache *layouts = nullptr;
     int device = 0;
     int64_t n = 0;
@@ -146,8 +158,8 @@ struct SmemLayout {
 }  // namespace
 
 struct SmemLayoutCache {
-    SmemLayout entry[4][3][3];
-    bool valid[4][3][3] = {};
+    SmemLayout entry[4][3][4];
+    bool valid[4][3][4] = {};
 };
 
 namespace {
@@ -448,6 +460,11 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
         if (K.timing) {
             if (c->timing_blocks < L.grid) {
                 if (c->d_timing) cudaFree(c->d_timing);
+    if (c->bins) {
+        if (c->bins->d_descs) cudaFree(c->bins->d_descs);
+        if (c->bins->h_descs) cudaFreeHost(c->bins->h_descs);
+        delete c->bins;
+    }
                 c->d_timing = nullptr;
                 c->timing_blocks = 0;
                 CUDA_TRY(cudaMalloc(&c->d_timing, (size_t)L.grid * 8 * sizeof(unsigned long long)));
@@ -602,6 +619,7 @@ int check_eval_args(const b200dpf_ctx *c, const void *keys, int64_t nkeys, int p
 {
     if (!c) return fail(B200DPF_EINVAL, "null context");
     if (!c->d_table && !c->multi) return fail(B200DPF_ESTATE, "context has no table");
+    if (c->bins) return fail(B200DPF_ESTATE, "grouped context: use b200dpf_group_eval");
     if (!keys || !out) return fail(B200DPF_EINVAL, "null buffer");
     if (nkeys < 1 || nkeys > (int64_t)1 << 24) return fail(B200DPF_EINVAL, "nkeys=%lld out of range", (long long)nkeys);
     if (prf < B200DPF_PRF_DUMMY || prf > B200DPF_PRF_AES128) return fail(B200DPF_EINVAL, "unknown prf id %d", prf);
@@ -881,6 +899,11 @@ int b200dpf_destroy(b200dpf_ctx *c)
     if (c->d_top_counters) cudaFree(c->d_top_counters);
     if (c->d_gridbar) cudaFree(c->d_gridbar);
     if (c->d_timing) cudaFree(c->d_timing);
+    if (c->bins) {
+        if (c->bins->d_descs) cudaFree(c->bins->d_descs);
+        if (c->bins->h_descs) cudaFreeHost(c->bins->h_descs);
+        delete c->bins;
+    }
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     if (c->d_frontier) cudaFree(c->d_frontier);
     if (c->d_leaf_cache) cudaFree(c->d_leaf_cache);
@@ -1426,6 +1449,244 @@ int b200dpf_create_multi(b200dpf_ctx **out, const int32_t *table, int64_t n, int
     *out = root;
     return B200DPF_OK;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Grouped evaluation: the batch-PIR front end.                  */
+/* ------------------------------------------------------------------------------------------- */
+int b200dpf_group_create(b200dpf_ctx **out, const int32_t *const *tables, const int64_t *n, int nbins, int entry_size,
+                         int device)
+{
+    if (!out) return fail(B200DPF_EINVAL, "null ctx out pointer");
+    *out = nullptr;
+    if (!tables || !n || nbins < 1 || nbins > (1 << 20)) return fail(B200DPF_EINVAL, "bad bin list (nbins=%d)", nbins);
+    if (entry_size < 1 || entry_size > 4096) return fail(B200DPF_EINVAL, "entry_size=%d out of range [1,4096]", entry_size);
+    int64_t n_max = 0, rows = 0;
+    for (int g = 0; g < nbins; g++) {
+        if (!tables[g]) return fail(B200DPF_EINVAL, "bin %d: null table", g);
+        if (n[g] < 2 || n[g] > ((int64_t)1 << 31) || (n[g] & (n[g] - 1)) != 0)
+            return fail(B200DPF_EINVAL, "bin %d: size n=%lld must be a power of two in [2, 2^31]", g, (long long)n[g]);
+        n_max = std::max(n_max, n[g]);
+        rows += n[g];
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(B200DPF_ECUDA, "no CUDA device available (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(B200DPF_EINVAL, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", device);
+
+    b200dpf_ctx *c = new (std::nothrow) b200dpf_ctx();
+    GroupBins *B = new (std::nothrow) GroupBins();
+    if (!c || !B) {
+        delete c;
+        delete B;
+        return fail(B200DPF_ENOMEM, "out of host memory");
+    }
+    c->bins = B;
+    c->device = device;
+    c->n = n_max;                       /* the launch plan (shared memory for correction words) is sized by the deepest bin */
+    c->depth = ilog2(n_max);
+    c->entry_size = entry_size;
+    c->entry_pad = (entry_size + 15) & ~15;       /* 16 columns per pass */
+    c->n_local = n_max;
+    c->depth_local = c->depth;
+#define GRP_TRY(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            fail(B200DPF_ECUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            b200dpf_destroy(c);                                                                \
+            return B200DPF_ECUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+    GRP_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    GRP_TRY(cudaDeviceGetAttribute(&c->coop_ok, cudaDevAttrCooperativeLaunch, device));
+    GRP_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    GRP_TRY(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    GRP_TRY(cudaMalloc(&c->d_gridbar, sizeof(uint32_t)));
+    GRP_TRY(cudaMemsetAsync(c->d_gridbar, 0, sizeof(uint32_t), c->stream));
+    GRP_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
+    GRP_TRY(upload_aes_table(host::aes_te0()));
+    if (!c->coop_ok) {
+        b200dpf_destroy(c);
+        return fail(B200DPF_ECUDA, "grouped evaluation needs cooperative launch support");
+    }
+    const size_t table_bytes = (size_t)rows * (size_t)c->entry_pad * sizeof(int32_t);
+    GRP_TRY(cudaMalloc(&c->d_table, table_bytes));
+    GRP_TRY(cudaMemsetAsync(c->d_table, 0, table_bytes, c->stream));
+    int32_t *d_stage = nullptr;
+    GRP_TRY(cudaMalloc(&d_stage, (size_t)n_max * entry_size * sizeof(int32_t)));
+    uint64_t row0 = 0;
+    cudaError_t e = cudaSuccess;
+    for (int g = 0; g < nbins && e == cudaSuccess; g++) {
+        /* each bin in its own breadth-first leaf order (bit reversal over ITS depth), 64-byte rows */
+        const int depth = ilog2(n[g]);
+        B->n.push_back(n[g]);
+        B->depth.push_back(depth);
+        B->row_off.push_back(row0);
+        e = cudaMemcpyAsync(d_stage, tables[g], (size_t)n[g] * entry_size * sizeof(int32_t), cudaMemcpyDefault, c->stream);
+        if (e == cudaSuccess)
+            e = launch_permute_table(d_stage, c->d_table + row0 * (uint64_t)c->entry_pad, (uint64_t)n[g], depth, entry_size,
+                                     c->entry_pad, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);    /* the staging buffer is reused */
+        row0 += (uint64_t)n[g];
+    }
+    cudaFree(d_stage);
+    GRP_TRY(e);
+#undef GRP_TRY
+    *out = c;
+    return B200DPF_OK;
+}
+
+int b200dpf_group_eval(b200dpf_ctx *c, const int32_t *keys, const int32_t *bins, int64_t nkeys, int prf, int32_t *out)
+{
+    if (!c || !c->bins) return fail(B200DPF_ESTATE, "not a grouped context (b200dpf_group_create)");
+    if (!keys || !bins || !out) return fail(B200DPF_EINVAL, "null buffer");
+    if (nkeys < 1 || nkeys > (int64_t)1 << 24) return fail(B200DPF_EINVAL, "nkeys=%lld out of range", (long long)nkeys);
+    if (prf < B200DPF_PRF_DUMMY || prf > B200DPF_PRF_AES128) return fail(B200DPF_EINVAL, "unknown prf id %d", prf);
+    GroupBins *B = c->bins;
+    const int nbins = (int)B->n.size();
+    /* counting sort by bin: a key group must not mix bins */
+    std::vector<int64_t> count((size_t)nbins + 1, 0);
+    for (int64_t b = 0; b < nkeys; b++) {
+        const int g = bins[b];
+        if (g < 0 || g >= nbins) return fail(B200DPF_EINVAL, "key %lld: bin %d out of range [0,%d)", (long long)b, g, nbins);
+        if (host::key_n(keys + b * host::KEY_WORDS) != B->n[(size_t)g])
+            return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, bin %d has n=%lld", (long long)b,
+                        (long long)host::key_n(keys + b * host::KEY_WORDS), g, (long long)B->n[(size_t)g]);
+        count[(size_t)g + 1]++;
+    }
+    for (int g = 0; g < nbins; g++) count[(size_t)g + 1] += count[(size_t)g];
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
+    int rc = ensure_host_keys(c, nkeys);
+    if (rc) return rc;
+    B->perm.assign((size_t)nkeys, 0);
+    {
+        std::vector<int64_t> next(count.begin(), count.end() - 1);
+        for (int64_t b = 0; b < nkeys; b++) {
+            const int64_t pos = next[(size_t)bins[b]]++;
+            B->perm[(size_t)pos] = b;
+            std::memcpy(c->h_keys + pos * host::KEY_WORDS, keys + b * host::KEY_WORDS, host::KEY_WORDS * sizeof(int32_t));
+        }
+    }
+    /* key groups and their work-item size: big items amortise the root-to-subtree walk every item
+     * pays (there is no frontier: bins are small), small items keep every warp busy */
+    SmemLayout L;
+    rc = smem_layout(c, prf, 4, MODE_GROUPED, &L);
+    if (rc) return rc;
+    const int64_t warps = (int64_t)L.grid * (L.threads / 32);
+    int64_t ngroups = 0;
+    for (int g = 0; g < nbins; g++) ngroups += (count[(size_t)g + 1] - count[(size_t)g] + 31) / 32;
+    int s_target = c->knobs.subtree_log2 > 0 ? c->knobs.subtree_log2 : 6;
+    s_target = std::min(s_target, L.s_max);
+    if (c->knobs.subtree_log2 <= 0) {
+        for (; s_target > 3; s_target--) {
+            int64_t items = 0;
+            for (int g = 0; g < nbins; g++) {
+                const int64_t kg = (count[(size_t)g + 1] - count[(size_t)g] + 31) / 32;
+                items += kg << std::max(0, B->depth[(size_t)g] - s_target);
+            }
+            if (items >= 2 * warps) break;
+        }
+    }
+    if ((size_t)ngroups > B->h_descs_cap) {
+        if (B->h_descs) cudaFreeHost(B->h_descs);
+        if (B->d_descs) cudaFree(B->d_descs);
+        B->h_descs = nullptr;
+        B->d_descs = nullptr;
+        B->h_descs_cap = B->descs_cap = 0;
+        const size_t cap = std::max<size_t>((size_t)ngroups, 1024);
+        CUDA_TRY(cudaMallocHost(&B->h_descs, cap * sizeof(GroupDesc)));
+        CUDA_TRY(cudaMalloc(&B->d_descs, cap * sizeof(GroupDesc)));
+        B->h_descs_cap = B->descs_cap = cap;
+    }
+    int s_max = 1;
+    {
+        int64_t gi = 0;
+        for (int g = 0; g < nbins; g++) {
+            const int depth = B->depth[(size_t)g];
+            const int s = std::max(1, std::min(depth, s_target));
+            for (int64_t k = count[(size_t)g]; k < count[(size_t)g + 1]; k += 32, gi++) {
+                GroupDesc &d = B->h_descs[gi];
+                d.key_first = (uint32_t)k;
+                d.nkeys = (uint32_t)std::min<int64_t>(32, count[(size_t)g + 1] - k);
+                d.depth = depth;
+                d.s = s;
+                d.nsub = (uint32_t)1 << (depth - s);
+                d.pad = 0;
+                d.table_off_v = B->row_off[(size_t)g] * (uint64_t)(c->entry_pad / 4);
+                s_max = std::max(s_max, s);
+            }
+        }
+    }
+    const int passes = c->entry_pad / 16;
+    const size_t key_bytes = (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t);
+    const size_t out_elems = (size_t)nkeys * c->entry_size;
+    rc = ensure_device_io(c, key_bytes, out_elems);
+    if (rc) return rc;
+    rc = ensure_host_out(c, out_elems);
+    if (rc) return rc;
+    const size_t n_counters = (size_t)passes * (size_t)ngroups;
+    rc = ensure_buffer(reinterpret_cast<void **>(&c->d_counters), &c->counters_cap, n_counters * sizeof(uint32_t));
+    if (rc) return rc;
+    if (c->has_last && c->last_stream != c->stream) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
+    CUDA_TRY(cudaMemcpyAsync(c->d_keys, c->h_keys, key_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(B->d_descs, B->h_descs, (size_t)ngroups * sizeof(GroupDesc), cudaMemcpyHostToDevice, c->stream));
+    if (c->coop_state_dirty) {
+        CUDA_TRY(cudaMemsetAsync(c->d_gridbar, 0, sizeof(uint32_t), c->stream));
+        c->bar_epoch = 0;
+        c->coop_state_dirty = false;
+    }
+    EvalParams p;
+    size_t smem;
+    fill_common(c, L, s_max, nkeys, 5, &p, &smem);
+    p.key_groups = (int)ngroups;
+    p.keys = reinterpret_cast<const uint4 *>(c->d_keys);
+    const KeyLayout kl = reference_layout();
+    p.key_stride_v = kl.stride_v; p.key_root_v = kl.root_v; p.key_compact = kl.compact;
+    p.groups = B->d_descs;
+    fill_phase(L, s_max, &p.main);
+    p.main.counters = c->d_counters;
+    p.out = reinterpret_cast<uint32_t *>(c->d_out);
+    /* one cooperative launch per 16 columns; the first one clears the result and every pass's tickets */
+    p.fuse_top = 1;
+    p.zero_a = p.out;
+    p.zero_a_words = out_elems;
+    p.zero_b = c->d_counters;
+    p.zero_b_words = n_counters;
+    c->last_launches = 0;
+    for (int pass = 0; pass < passes; pass++) {
+        p.col_off_v = (uint32_t)(pass * 4);
+        p.col_off = (uint32_t)(pass * 16);
+        p.ncols = (uint32_t)std::max(0, std::min(16, c->entry_size - pass * 16));
+        if (p.ncols == 0) break;
+        p.main.counters = c->d_counters + (size_t)pass * (size_t)ngroups;
+        if (p.fuse_top) {
+            p.grid_bar = c->d_gridbar;
+            c->bar_epoch += (uint32_t)L.grid;
+            p.grid_bar_target = c->bar_epoch;
+        }
+        const cudaError_t e = launch_eval(prf, 4, MODE_GROUPED, p, L.grid, smem, c->stream);
+        if (e != cudaSuccess) {
+            c->coop_state_dirty = true;
+            return fail(B200DPF_ECUDA, "grouped evaluation launch: %s", cudaGetErrorString(e));
+        }
+        c->last_launches++;
+        p.fuse_top = 0;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_done, c->stream));
+    c->last_stream = c->stream;
+    c->has_last = true;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    for (int64_t pos = 0; pos < nkeys; pos++)       /* back to the caller's order */
+        std::memcpy(out + B->perm[(size_t)pos] * c->entry_size, c->h_out + pos * c->entry_size, sizeof(int32_t) * (size_t)c->entry_size);
+    return B200DPF_OK;
+}
+
+int b200dpf_group_bins(const b200dpf_ctx *c) { return (c && c->bins) ? (int)c->bins->n.size() : 0; }
+
 
 int b200dpf_ctx_read_timing(b200dpf_ctx *c, uint64_t *stamps, int max_blocks, int *nblocks)
 {

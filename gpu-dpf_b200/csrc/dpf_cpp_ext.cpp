@@ -149,6 +149,43 @@ std::vector<void *> eval_init_multi(const at::Tensor &table, const std::vector<i
     return {static_cast<void *>(ctx)};
 }
 
+/* batch PIR: many tables ("bins") of one entry size behind one context (b200dpf_group_create) */
+std::vector<void *> group_init(const std::vector<at::Tensor> &tables, int device)
+{
+    TORCH_CHECK(!tables.empty(), "group_init: no tables");
+    std::vector<at::Tensor> keep;
+    std::vector<const int32_t *> ptrs;
+    std::vector<int64_t> sizes;
+    for (const at::Tensor &t : tables) {
+        TORCH_CHECK(t.dim() == 2 && t.size(1) == tables[0].size(1), "group_init: tables must be [n_g, entry_size] with one entry_size");
+        keep.push_back(t.to(at::kInt).contiguous().cpu());
+        ptrs.push_back(keep.back().data_ptr<int32_t>());
+        sizes.push_back(keep.back().size(0));
+    }
+    b200dpf_ctx *ctx = nullptr;
+    check(b200dpf_group_create(&ctx, ptrs.data(), sizes.data(), (int)ptrs.size(), (int)tables[0].size(1), device), "group_init");
+    return {static_cast<void *>(ctx)};
+}
+
+/* keys int32 [B,524], bins int32/int64 [B] -> int32 [B, E]: key b evaluated on table bins[b] */
+at::Tensor group_eval(const at::Tensor &keys, const at::Tensor &bins, const std::vector<void *> &buffers, int prf)
+{
+    b200dpf_ctx *ctx = ctx_of(buffers);
+    TORCH_CHECK(keys.device().is_cpu() && keys.scalar_type() == at::kInt && keys.dim() == 2 && keys.size(1) == kKeyWords &&
+                    keys.is_contiguous(),
+                "group_eval: keys must be a contiguous CPU int32 tensor [B, 524]");
+    at::Tensor b32 = bins.to(at::kInt).contiguous().cpu();
+    TORCH_CHECK(b32.dim() == 1 && b32.size(0) == keys.size(0), "group_eval: one bin index per key");
+    at::Tensor result = torch::empty({keys.size(0), (int64_t)b200dpf_ctx_entry_size(ctx)}, at::kInt);
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_group_eval(ctx, keys.data_ptr<int32_t>(), b32.data_ptr<int32_t>(), keys.size(0), prf,
+                                 result.data_ptr<int32_t>()),
+              "group_eval");
+    }
+    return result;
+}
+
 /* "all" / "" -> every visible device; "0,2,3" -> that list */
 std::vector<int> parse_devices(const std::string &spec)
 {
@@ -349,6 +386,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           py::arg("prf"), py::arg("nthreads") = 0);
     m.def("eval_init_sharded", &eval_init_sharded, "eval_init for one entry-range shard", py::arg("table"),
           py::arg("device"), py::arg("shard_rank"), py::arg("shard_count"));
+    m.def("group_init", &group_init, "batch PIR: one context over many tables (bins)", py::arg("tables"), py::arg("device") = 0);
+    m.def("group_eval", &group_eval, "batch PIR: evaluate (bin, key) pairs in one launch");
     m.def("eval_init_multi", &eval_init_multi, "eval_init over several GPUs of this process", py::arg("table"),
           py::arg("devices"), py::arg("axis") = 0);
     m.def("parse_devices", &parse_devices, "'all' or '0,1,2' -> device list");

@@ -135,9 +135,11 @@ struct DevEnv {
         const uint4 v = *slot(h);
         return make_seed(v.x, v.y, v.z, v.w);
     }
+    static constexpr bool MAC = (MODE == MODE_FUSED || MODE == MODE_GROUPED);   /* leaves feed the inner product */
+
     __device__ __forceinline__ void leaf_prefetch(uint32_t local_pos)
     {
-        if (MODE == MODE_FUSED) {
+        if (MAC) {
             const uint4 *r = rows + (size_t)local_pos * row_stride_v;
 #pragma unroll
             for (int j = 0; j < 4; j++) ra[j] = __ldg(r + j);
@@ -147,7 +149,7 @@ struct DevEnv {
     }
     __device__ __forceinline__ void leaf_pair(uint32_t local_pos, uint32_t v0, uint32_t v1)
     {
-        if (MODE == MODE_FUSED) {
+        if (MAC) {
             if (leaf_out != nullptr) {   /* coalesced: 32 keys x 4 bytes per leaf */
                 leaf_out[(size_t)local_pos * 32] = v0;
                 leaf_out[(size_t)(local_pos + 1) * 32] = v1;
@@ -259,24 +261,42 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
     env.row_stride_v = p.row_stride_v;
     env.depth = p.depth;
 
+    constexpr bool GROUPED = (MODE == MODE_GROUPED);
     uint32_t taken = 0;
     for (int j = 0; j < p.key_groups; j++) {
         const int kg = (int)((blockIdx.x + (unsigned)j) % (unsigned)p.key_groups);
 
+        /* what this key group evaluates: the context's one table, or (grouped) its own bin */
+        int g_depth = p.depth, g_s = ph.s, g_walk_first = ph.walk_first_level, g_walk_steps = ph.walk_steps;
+        int g_key_first = kg * kpw, g_key_last = p.nkeys - 1;
+        uint32_t g_tickets = ntickets;
+        const uint4 *g_table = p.table;
+        if (GROUPED) {
+            const GroupDesc g = p.groups[kg];
+            g_depth = g.depth;
+            g_s = g.s;
+            g_walk_first = g.depth - 1;
+            g_walk_steps = g.depth - g.s;
+            g_key_first = (int)g.key_first;
+            g_key_last = (int)(g.key_first + g.nkeys) - 1;
+            g_tickets = g.nsub;
+            g_table = p.table + g.table_off_v;
+        }
+
         if (quota != 0xffffffffu && __syncthreads_and(taken >= quota)) break;   /* the block's share is done */
-        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(ph.counters + kg) < ntickets) ? 1 : 0;
+        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(ph.counters + kg) < g_tickets) ? 1 : 0;
         __syncthreads();
         const bool has_work = (*flag_s != 0);
         if (has_work) {
             /* correction words of this key group -> shared, [level][bank][bit][key] */
-            const int per_key = p.depth * 4;
+            const int per_key = g_depth * 4;
             for (int i = tid; i < per_key * kpw; i += THREADS) {
                 const int k = i / per_key;            /* key within the group   */
                 const int e = i - k * per_key;        /* (bank, level, bit)     */
-                const int bank = e / (p.depth * 2);
-                const int lb = e - bank * (p.depth * 2);   /* 2*level + bit       */
-                int key = kg * kpw + k;
-                if (key >= p.nkeys) key = p.nkeys - 1;
+                const int bank = e / (g_depth * 2);
+                const int lb = e - bank * (g_depth * 2);   /* 2*level + bit       */
+                int key = g_key_first + k;
+                if (key > g_key_last) key = g_key_last;
                 const int level = lb >> 1, bit = lb & 1;
                 const uint32_t slot = p.key_compact ? 2u + 4u * (uint32_t)level + 2u * (uint32_t)bank + (uint32_t)bit
                                                     : (bank ? 65u : 1u) + (uint32_t)lb;
@@ -285,17 +305,17 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
                 if (level == 0) cwlo_s[(bank * 2 + bit) * 32 + k] = v.x;
             }
             if (tid < kpw) {
-                int key = kg * kpw + tid;
-                if (key >= p.nkeys) key = p.nkeys - 1;
+                int key = g_key_first + tid;
+                if (key > g_key_last) key = g_key_last;
                 root_s[tid] = __ldg(p.keys + (size_t)key * p.key_stride_v + p.key_root_v);
             }
         }
         __syncthreads();
         if (!has_work) continue;
 
-        const int key = kg * kpw + kslot;
-        env.key_valid = key < p.nkeys;
-        if (MODE == MODE_FUSED) {
+        const int key = g_key_first + kslot;
+        env.key_valid = key <= g_key_last;
+        if (MODE == MODE_FUSED || GROUPED) {
 #pragma unroll
             for (int e = 0; e < 4 * NV; e++) env.acc[e] = 0;
         } else if (MODE == MODE_EXPAND) {
@@ -309,7 +329,7 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
             uint32_t t = 0;
             if (lane == 0) t = atomicAdd(ph.counters + kg, 1u);
             t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= ntickets) break;
+            if (t >= g_tickets) break;
             taken++;
             const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
@@ -319,20 +339,20 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
                 const uint4 fv = __ldcg(ph.frontier_in + ((size_t)kg * p.nfront + (q >> ph.front_shift)) * kpw + kslot);
                 start = make_seed(fv.x, fv.y, fv.z, fv.w);
             }
-            const Seed r = walk_down<PRF>(env, start, ph.walk_first_level, ph.walk_steps, ph.sub_first + q);
+            const Seed r = walk_down<PRF>(env, start, g_walk_first, g_walk_steps, ph.sub_first + q);
             if (MODE == MODE_FRONTIER) {
-                env.front_out = p.frontier_out + ((size_t)kg * p.nfront + ((size_t)q << ph.s)) * kpw + kslot;
-                eval_subtree<PRF, true>(env, r, ph.s, ph.level_base);
+                env.front_out = p.frontier_out + ((size_t)kg * p.nfront + ((size_t)q << g_s)) * kpw + kslot;
+                eval_subtree<PRF, true>(env, r, g_s, ph.level_base);
             } else {
-                env.rows = p.table + ((size_t)q << ph.s) * p.row_stride_v + p.col_off_v;
-                env.pos_base = (ph.sub_first + q) << ph.s;
-                env.leaf_out = p.leaf_cache ? p.leaf_cache + ((size_t)kg * p.n_local + ((size_t)q << ph.s)) * 32 + lane
-                                            : nullptr;
-                eval_subtree<PRF, false>(env, r, ph.s, 0);
+                env.rows = g_table + ((size_t)q << g_s) * p.row_stride_v + p.col_off_v;
+                env.pos_base = (ph.sub_first + q) << g_s;
+                env.leaf_out = (!GROUPED && p.leaf_cache) ? p.leaf_cache + ((size_t)kg * p.n_local + ((size_t)q << g_s)) * 32 + lane
+                                                          : nullptr;
+                eval_subtree<PRF, false>(env, r, g_s, 0);
             }
         }
 
-        if (MODE == MODE_FUSED) {
+        if (MODE == MODE_FUSED || GROUPED) {
             /* lanes that hold the same key (different subtree slots) fold their partial sums
              * first, so every key receives one red.add per warp and column, not 32/kpw */
             for (int off = kpw; off < 32; off <<= 1) {
@@ -681,12 +701,14 @@ cudaError_t max_smem_one(int *bytes)
     return cudaSuccess;
 }
 
-/* (prf, nv, mode) -> instantiation; modes 1 and 2 never touch the table, so NV = 4 only */
+/* (prf, nv, mode) -> instantiation; modes 1 and 2 never touch the table, so NV = 4 only; grouped
+ * evaluation takes 16 columns per pass */
 template <int PRF>
 cudaError_t launch_prf(int nv, int mode, const EvalParams &p, int grid, size_t smem, cudaStream_t stream)
 {
     if (mode == MODE_EXPAND) return launch_one<PRF, 4, MODE_EXPAND>(p, grid, smem, stream);
     if (mode == MODE_FRONTIER) return launch_one<PRF, 4, MODE_FRONTIER>(p, grid, smem, stream);
+    if (mode == MODE_GROUPED) return launch_one<PRF, 4, MODE_GROUPED>(p, grid, smem, stream);
     if (nv == 4) return launch_one<PRF, 4, MODE_FUSED>(p, grid, smem, stream);
     if (nv == 8) return launch_one<PRF, 8, MODE_FUSED>(p, grid, smem, stream);
     if (nv == 16) return launch_one<PRF, 16, MODE_FUSED>(p, grid, smem, stream);
@@ -698,6 +720,7 @@ cudaError_t max_smem_prf(int nv, int mode, int *bytes)
 {
     if (mode == MODE_EXPAND) return max_smem_one<PRF, 4, MODE_EXPAND>(bytes);
     if (mode == MODE_FRONTIER) return max_smem_one<PRF, 4, MODE_FRONTIER>(bytes);
+    if (mode == MODE_GROUPED) return max_smem_one<PRF, 4, MODE_GROUPED>(bytes);
     if (nv == 4) return max_smem_one<PRF, 4, MODE_FUSED>(bytes);
     if (nv == 8) return max_smem_one<PRF, 8, MODE_FUSED>(bytes);
     if (nv == 16) return max_smem_one<PRF, 16, MODE_FUSED>(bytes);

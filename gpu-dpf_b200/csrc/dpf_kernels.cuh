@@ -28,6 +28,19 @@ struct PhaseParams {
                                  region, the rest in the hi region                      */
 };
 
+/* Grouped evaluation (batch PIR: many small tables -- "bins" -- behind one context, one launch for a
+ * mixed list of (bin, key) pairs): a key group is <= 32 keys of the SAME bin, so its warp still
+ * walks one tree shape and shares each table row.  One descriptor per key group. */
+struct GroupDesc {
+    uint32_t key_first;       /* first key of the group in the (bin-sorted) key array       */
+    uint32_t nkeys;           /* 1..32                                                      */
+    int32_t depth;            /* log2 of the bin's table size                               */
+    int32_t s;                /* log2 leaves per work item for this group                   */
+    uint32_t nsub;            /* work items (2^s-leaf subtrees) = 2^(depth - s)             */
+    uint32_t pad;
+    uint64_t table_off_v;     /* bin's first row, in uint4 units from EvalParams::table     */
+};
+
 /* Parameters of one evaluation launch (one pass over <= 16*NVMAX columns). */
 struct EvalParams {
     const uint4 *keys;        /* [nkeys] keys, key_stride_v 128-bit slots apart          */
@@ -49,6 +62,7 @@ struct EvalParams {
     uint32_t col_off;         /* first int32 column of this pass                        */
     uint32_t ncols;           /* valid int32 columns in this pass (<= 4*NV)             */
     int depth;                /* log2 n                                                 */
+    const GroupDesc *groups;  /* MODE_GROUPED: [key_groups] descriptors (else null)      */
     PhaseParams main;         /* the phase that produces the result (or, in the stand-alone
                                  frontier kernel, the frontier)                          */
     /* single-launch pipeline: the launch first clears its own accumulators and ticket
@@ -92,7 +106,7 @@ struct EvalParams {
 };
 
 /* Kernel modes. */
-enum { MODE_FUSED = 0, MODE_EXPAND = 1, MODE_FRONTIER = 2 };
+enum { MODE_FUSED = 0, MODE_EXPAND = 1, MODE_FRONTIER = 2, MODE_GROUPED = 3 };
 
 /* Threads per block / minimum blocks per SM of the kernel instantiated for
  * (prf, nv) where nv = uint4 (4 int32 columns) of a table row handled per pass:

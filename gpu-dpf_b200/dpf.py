@@ -256,6 +256,50 @@ class DPF(object):
             self.table_num_entries, self.table_effective_entry_size, self.prf_method_string)
 
 
+class BinnedDPF(DPF):
+    """Batch PIR (the paper's co-design front end, paper/experimental/batch_pir/batch_pir_optimization.py:84-87,
+    210-218, which the reference only costs analytically): the table is split into bins, a query carries one DPF
+    key per bin it touches, and the server evaluates all (bin, key) pairs of a batch of queries in ONE launch.
+
+        d = BinnedDPF(prf=DPF.PRF_AES128)
+        d.eval_init([bin0, bin1, ...])           # tables [n_g, entry_size], power-of-two n_g >= 2
+        k1, k2 = d.gen_in_bin(g, index)          # keys for entry `index` of bin g
+        shares = d.eval_gpu(keys, bins)          # int32 [len(keys), entry_size]
+    """
+
+    def eval_init(self, tables):
+        if self.buffers is not None:
+            dpf_cpp.eval_free(self.buffers)
+            self.buffers = None
+        tables = list(tables)
+        for t in tables:
+            if t.shape[0] & (t.shape[0] - 1) != 0 or t.shape[0] < 2:
+                raise Exception("Table num entries (%d) must be a power of two" % (t.shape[0]))
+        self.bin_sizes = [int(t.shape[0]) for t in tables]
+        self.table = None
+        self.table_num_entries = sum(self.bin_sizes)
+        self.table_effective_entry_size = tables[0].shape[1]
+        self.buffers = dpf_cpp.group_init(tables, self.device)
+
+    def gen_in_bin(self, g, k, seed=None, secure=False):
+        return self.gen(k, self.bin_sizes[g], seed=seed, secure=secure)
+
+    def eval_gpu(self, keys, bins):
+        if self.buffers is None:
+            raise Exception("Must call `eval_init` before `eval_gpu`")
+        if not isinstance(keys, torch.Tensor):
+            if len(keys) == 0:
+                return torch.zeros((0, self.table_effective_entry_size), dtype=torch.int32)
+            keys = torch.stack(list(keys))
+        return dpf_cpp.group_eval(keys.contiguous(), torch.as_tensor(bins), self.buffers, self.prf_method)
+
+    def __repr__(self):
+        if self.buffers is None:
+            return "BinnedDPF(_uninitialized_, prf_method=%s)" % self.prf_method_string
+        return "BinnedDPF(bins=%d, entries=%d, entry_size=%d, prf_method=%s)" % (
+            len(self.bin_sizes), self.table_num_entries, self.table_effective_entry_size, self.prf_method_string)
+
+
 def _next_pow2(n):
     return 1 << max(1, (n - 1).bit_length())
 

@@ -179,6 +179,23 @@ int b200dpf_create_multi(b200dpf_ctx **ctx, const int32_t *table, int64_t n, int
 int b200dpf_ctx_device_count(const b200dpf_ctx *ctx);
 int b200dpf_ctx_axis(const b200dpf_ctx *ctx);
 
+/*
+ * Grouped evaluation -- the batch-PIR front end (the reference only
+ * models it analytically: paper/experimental/batch_pir/batch_pir_optimization.py:84-87 charges one
+ * DPF over every bin per query, :210-218 sums them).  One context holds `nbins` tables ("bins") of
+ * possibly different power-of-two sizes n[g] (same entry_size); b200dpf_group_eval evaluates a mixed
+ * list of (bin, key) pairs -- key b against table bins[b] -- in ONE launch: keys are sorted by bin,
+ * cut into groups of <= 32 keys of one bin, and the work items of all groups form one ticket space,
+ * so many small bins fill the GPU the way one big table does.
+ *   out[b][e] = the same inner product b200dpf_eval would give for key b on table bins[b].
+ * tables[g]: int32 [n[g]][entry_size], host or device.  keys: int32[nkeys][524]; bins: int32[nkeys].
+ */
+int b200dpf_group_create(b200dpf_ctx **ctx, const int32_t *const *tables, const int64_t *n, int nbins,
+                         int entry_size, int device);
+int b200dpf_group_eval(b200dpf_ctx *ctx, const int32_t *keys, const int32_t *bins, int64_t nkeys, int prf,
+                       int32_t *out);
+int b200dpf_group_bins(const b200dpf_ctx *ctx);
+
 /* Replaces: dpf_cpp.eval_free -> eval_free()               dpf_wrapper.cu:86-91. */
 int b200dpf_destroy(b200dpf_ctx *ctx);
 
