@@ -130,6 +130,9 @@ struct b200dpf_ctx {
         int one_launch = 1;        /* B200DPF_ONE_LAUNCH     whole evaluation as one cooperative launch    */
         int balance_top = 1;       /* B200DPF_BALANCE_TOP    even per-block shares of the tree-top phase    */
         int timing = 0;            /* B200DPF_TIMING         per-block phase time stamps (diagnostics)      */
+        int tma_rows = 0;          /* B200DPF_TMA_ROWS       fused kernel: stage each item's rows with cp.async.bulk
+                                                             (16-column tables, Salsa/ChaCha/dummy); measured slower than
+                                                             broadcast loads -- profiles/r2_tma_rows_ab.txt -- so off */
     } knobs;
     unsigned long long *d_timing = nullptr;   /* [timing_blocks][8] */
     int timing_blocks = 0;
@@ -150,6 +153,7 @@ namespace {
 
 struct SmemLayout {
     int threads, blocks_per_sm, grid;
+    int budget;               /* dynamic shared memory one block may use */
     size_t smem_fixed;        /* AES: whole budget; others: computed from s */
     uint32_t off_meta, off_lo, off_hi, off_tab, meta_cw, level_bytes;
     int cap_lo, cap_hi, s_max;
@@ -158,8 +162,8 @@ struct SmemLayout {
 }  // namespace
 
 struct SmemLayoutCache {
-    SmemLayout entry[4][3][4];
-    bool valid[4][3][4] = {};
+    SmemLayout entry[4][3][5];
+    bool valid[4][3][5] = {};
 };
 
 namespace {
@@ -197,6 +201,7 @@ int smem_layout_compute(b200dpf_ctx *c, int prf, int nv, int mode, SmemLayout *L
     /* every resident block also pays the 1 KiB system reservation */
     int budget = std::min(max_smem, sm_total / L->blocks_per_sm - 1024);
     budget &= ~15;
+    L->budget = budget;
 
     L->meta_cw = (uint32_t)c->depth * 4u * 32u * 16u;
     const uint32_t meta = L->meta_cw + 512u + 512u + 16u;
@@ -306,8 +311,12 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
      * entries use one tree expansion per 64 columns. */
     const int nv = (mode_main != MODE_FUSED || c->entry_pad <= 16 || want_cache) ? 4 : (c->entry_pad <= 32 ? 8 : 16);
     const int passes = mode_main == MODE_FUSED ? (want_cache ? 1 : c->entry_pad / (4 * nv)) : 1;
+    /* optional variant: the rows of each work item staged into shared memory by cp.async.bulk */
+    bool tma_rows = K.tma_rows != 0 && K.one_launch != 0 && c->coop_ok != 0 && mode_main == MODE_FUSED && c->entry_pad == 16 &&
+                    prf != B200DPF_PRF_AES128 && nkeys >= 17;
+    int mode_kernel = tma_rows ? MODE_FUSED_TMA : mode_main;
     SmemLayout L;
-    int rc = smem_layout(c, prf, nv, mode_main, &L);
+    int rc = smem_layout(c, prf, nv, mode_kernel, &L);
     if (rc) return rc;
     const int64_t warps = (int64_t)L.grid * (L.threads / 32);
     /* keys per warp: a full warp of keys when the batch allows; for small batches the
@@ -340,6 +349,20 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
             s--;
     }
     if (s < 1) s = 1;
+    size_t tile_bytes = 0;
+    if (tma_rows) {
+        /* one tile of 2^s 64-byte rows per warp, after the sibling stack */
+        const int warps_blk = L.threads / 32;
+        if (K.subtree_log2 <= 0) s = std::min(s, 6);
+        tile_bytes = (size_t)warps_blk * ((size_t)64 << s) + 8u * (size_t)warps_blk + 16u;
+        if ((size_t)L.off_lo + (size_t)(std::max(s, 5) - 1) * L.level_bytes + tile_bytes > (size_t)L.budget) {
+            tma_rows = false;               /* does not fit beside correction words and stack: broadcast loads */
+            mode_kernel = mode_main;
+            tile_bytes = 0;
+            rc = smem_layout(c, prf, nv, mode_kernel, &L);
+            if (rc) return rc;
+        }
+    }
     const int rel = c->depth_local - s;           /* tree levels between the shard root and the items */
     if (5 - kpw_log2 > rel) {                     /* not enough subtrees to split a warp that far */
         kpw_log2 = 5 - rel;
@@ -426,6 +449,11 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
     fill_common(c, L, std::max(s, s_top), nkeys, kpw_log2, &p, &smem);
     p.keys = reinterpret_cast<const uint4 *>(keys_dev);
     p.key_stride_v = kl.stride_v; p.key_root_v = kl.root_v; p.key_compact = kl.compact;
+    if (tma_rows) {
+        p.off_tile = (uint32_t)((smem + 15) & ~(size_t)15);
+        p.off_tile_bar = p.off_tile + (uint32_t)((size_t)(L.threads / 32) * ((size_t)64 << s));
+        smem = (size_t)p.off_tile + tile_bytes;
+    }
     fill_phase(L, s, &p.main);
     p.main.nsub = (uint32_t)1 << rel;
     p.main.sub_first = (uint32_t)c->shard_rank << rel;
@@ -545,7 +573,7 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
         p.ncols = (uint32_t)std::max(0, std::min(4 * nv, c->entry_size - pass * 4 * nv));
         if (p.ncols == 0) break;
         p.main.counters = c->d_counters + (size_t)pass * key_groups;
-        rc = launch_main(nv, MODE_FUSED);
+        rc = launch_main(nv, mode_kernel);
         if (rc) return rc;
     }
     return B200DPF_OK;
@@ -803,6 +831,7 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     c->knobs.one_launch = env_int("B200DPF_ONE_LAUNCH", c->knobs.one_launch);
     c->knobs.balance_top = env_int("B200DPF_BALANCE_TOP", c->knobs.balance_top);
     c->knobs.timing = env_int("B200DPF_TIMING", c->knobs.timing);
+    c->knobs.tma_rows = env_int("B200DPF_TMA_ROWS", c->knobs.tma_rows);
     CTX_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
     CTX_TRY(upload_aes_table(host::aes_te0()));
 
@@ -1149,6 +1178,7 @@ int b200dpf_ctx_set_option(b200dpf_ctx *c, const char *name, int value)
         {"frontier_mb", &c->knobs.frontier_mb, 1, 1 << 16}, {"subtree_log2", &c->knobs.subtree_log2, 0, 16},
         {"mac_tma", &c->knobs.mac_tma, 0, 1},             {"one_launch", &c->knobs.one_launch, 0, 1},
         {"balance_top", &c->knobs.balance_top, 0, 1},     {"timing", &c->knobs.timing, 0, 1},
+        {"tma_rows", &c->knobs.tma_rows, 0, 1},
     };
     for (auto &o : opts)
         if (std::strcmp(o.name, name) == 0) {

@@ -91,6 +91,38 @@ struct NoTables {
 template <int PRF> struct TablePolicy { typedef NoTables type; };
 template <> struct TablePolicy<PRF_AES128> { typedef AesSmemTables type; };
 
+/* ---- cp.async.bulk (TMA) + mbarrier primitives ----------------------------- */
+namespace tma {
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1u << 28)) __trap();   /* a lost arrival must not hang the GPU */
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+}  // namespace tma
+
 /* ---- per-thread environment for the shared traversal code ---------------- */
 template <int PRF, int NV, int THREADS, int MODE>
 struct DevEnv {
@@ -135,11 +167,29 @@ struct DevEnv {
         const uint4 v = *slot(h);
         return make_seed(v.x, v.y, v.z, v.w);
     }
-    static constexpr bool MAC = (MODE == MODE_FUSED || MODE == MODE_GROUPED);   /* leaves feed the inner product */
+    static constexpr bool MAC = (MODE == MODE_FUSED || MODE == MODE_GROUPED || MODE == MODE_FUSED_TMA);   /* leaves feed the inner product */
+    static constexpr bool STAGED = (MODE == MODE_FUSED_TMA);
+    /* STAGED: the work item's 2^s rows were requested with one cp.async.bulk when the item was drawn;
+     * they are first needed s-1 node expansions later, which hides the copy */
+    const uint4 *tile;          /* this warp's staged rows (shared memory) */
+    uint32_t tile_bar;          /* shared-window address of this warp's mbarrier */
+    uint32_t tile_phase;
+    bool tile_pending;
 
     __device__ __forceinline__ void leaf_prefetch(uint32_t local_pos)
     {
-        if (MAC) {
+        if (STAGED) {
+            if (tile_pending) {
+                tma::mbar_wait(tile_bar, tile_phase);
+                tile_phase ^= 1u;
+                tile_pending = false;
+            }
+            const uint4 *r = tile + (size_t)local_pos * 4;
+#pragma unroll
+            for (int j = 0; j < 4; j++) ra[j] = r[j];
+#pragma unroll
+            for (int j = 0; j < 4; j++) rb[j] = r[4 + j];
+        } else if (MAC) {
             const uint4 *r = rows + (size_t)local_pos * row_stride_v;
 #pragma unroll
             for (int j = 0; j < 4; j++) ra[j] = __ldg(r + j);
@@ -260,6 +310,18 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
     env.stack_split = ph.stack_split;
     env.row_stride_v = p.row_stride_v;
     env.depth = p.depth;
+    if constexpr (MODE == MODE_FUSED_TMA) {
+        const int w = tid >> 5;
+        env.tile = reinterpret_cast<const uint4 *>(g_dyn_smem + p.off_tile + ((size_t)w << (ph.s + 6)));
+        env.tile_bar = (uint32_t)__cvta_generic_to_shared(g_dyn_smem + p.off_tile_bar + 8 * w);
+        env.tile_phase = 0;
+        env.tile_pending = false;
+        if (lane == 0) {
+            tma::mbar_init(env.tile_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
 
     constexpr bool GROUPED = (MODE == MODE_GROUPED);
     uint32_t taken = 0;
@@ -315,7 +377,7 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
 
         const int key = g_key_first + kslot;
         env.key_valid = key <= g_key_last;
-        if (MODE == MODE_FUSED || GROUPED) {
+        if (MODE == MODE_FUSED || MODE == MODE_FUSED_TMA || GROUPED) {
 #pragma unroll
             for (int e = 0; e < 4 * NV; e++) env.acc[e] = 0;
         } else if (MODE == MODE_EXPAND) {
@@ -324,13 +386,17 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
         const uint4 rv = root_s[kslot];
         const Seed root = make_seed(rv.x, rv.y, rv.z, rv.w);
 
-        for (;;) {
-            if (taken >= quota) break;
-            uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(ph.counters + kg, 1u);
-            t = __shfl_sync(0xffffffffu, t, 0);
+        /* tickets are drawn one item ahead, so the atomic's round trip to L2 overlaps the item being
+         * expanded instead of stalling the warp between items (items can be as small as 7 node pairs) */
+        uint32_t t_raw = 0;
+        bool draw = taken < quota;
+        if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, 1u);
+        while (draw) {
+            const uint32_t t = __shfl_sync(0xffffffffu, t_raw, 0);
             if (t >= g_tickets) break;
             taken++;
+            draw = taken < quota;
+            if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, 1u);
             const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
             if (ph.frontier_in != nullptr) {
@@ -345,6 +411,17 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
                 eval_subtree<PRF, true>(env, r, g_s, ph.level_base);
             } else {
                 env.rows = g_table + ((size_t)q << g_s) * p.row_stride_v + p.col_off_v;
+                if constexpr (MODE == MODE_FUSED_TMA) {
+                    /* the item's rows are one contiguous run (64-byte rows, breadth-first leaf order) */
+                    __syncwarp();                                   /* every lane is done with the previous tile */
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        const uint32_t bytes = 64u << g_s;
+                        tma::mbar_expect_tx(env.tile_bar, bytes);
+                        tma::bulk_g2s((uint32_t)__cvta_generic_to_shared(const_cast<uint4 *>(env.tile)), env.rows, bytes, env.tile_bar);
+                    }
+                    env.tile_pending = true;
+                }
                 env.pos_base = (ph.sub_first + q) << g_s;
                 env.leaf_out = (!GROUPED && p.leaf_cache) ? p.leaf_cache + ((size_t)kg * p.n_local + ((size_t)q << g_s)) * 32 + lane
                                                           : nullptr;
@@ -352,7 +429,7 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
             }
         }
 
-        if (MODE == MODE_FUSED || GROUPED) {
+        if (MODE == MODE_FUSED || MODE == MODE_FUSED_TMA || GROUPED) {
             /* lanes that hold the same key (different subtree slots) fold their partial sums
              * first, so every key receives one red.add per warp and column, not 32/kpw */
             for (int off = kpw; off < 32; off <<= 1) {
@@ -408,7 +485,16 @@ dpf_eval_kernel(const __grid_constant__ EvalParams p)
                  * quota%nwarps warps); round 2: whatever is left, first come first served */
                 constexpr uint32_t NW = THREADS / 32;
                 const uint32_t w = (uint32_t)tid >> 5;
-                run_phase<PRF, 4, THREADS, MODE_FRONTIER>(p, p.top, ta, p.top_block_quota / NW + (w < p.top_block_quota % NW ? 1u : 0u));
+                uint32_t bq = p.top_block_quota;
+                const uint32_t kgs = (uint32_t)p.key_groups;
+                if (bq != 0x7fffffffu && gridDim.x >= kgs) {
+                    /* blocks start at key group blockIdx % key_groups: the nb blocks that start at a
+                     * group share its tickets exactly, so round 1 leaves nothing behind */
+                    const uint32_t nb = gridDim.x / kgs + ((blockIdx.x % kgs) < (gridDim.x % kgs) ? 1u : 0u);
+                    const uint32_t tickets = p.top.nsub >> (5 - p.kpw_log2);
+                    bq = (tickets + nb - 1) / nb;
+                }
+                run_phase<PRF, 4, THREADS, MODE_FRONTIER>(p, p.top, ta, bq / NW + (w < bq % NW ? 1u : 0u));
                 run_phase<PRF, 4, THREADS, MODE_FRONTIER>(p, p.top, ta);
             }
             if (stamp) stamp[2] = global_ns();
@@ -495,36 +581,6 @@ __global__ void __launch_bounds__(256, 2) dpf_mac_kernel(const __grid_constant__
  * so a row slice staged once is multiplied against 8 x 32 keys -- do LDS + IMAD only.  The
  * register-staged variant above is latency bound (16 dependent load phases per trip); this one
  * is bound by the FMA pipe. */
-namespace tma {
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; spin++) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1u << 28)) __trap();   /* a lost arrival must not hang the GPU */
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-}  // namespace tma
 
 template <int NV>
 struct MacTmaShape {
@@ -709,6 +765,10 @@ cudaError_t launch_prf(int nv, int mode, const EvalParams &p, int grid, size_t s
     if (mode == MODE_EXPAND) return launch_one<PRF, 4, MODE_EXPAND>(p, grid, smem, stream);
     if (mode == MODE_FRONTIER) return launch_one<PRF, 4, MODE_FRONTIER>(p, grid, smem, stream);
     if (mode == MODE_GROUPED) return launch_one<PRF, 4, MODE_GROUPED>(p, grid, smem, stream);
+    if (mode == MODE_FUSED_TMA) {
+        if constexpr (PRF == PRF_AES128) return cudaErrorInvalidValue;    /* no shared memory left beside the tables */
+        else return launch_one<PRF, 4, MODE_FUSED_TMA>(p, grid, smem, stream);
+    }
     if (nv == 4) return launch_one<PRF, 4, MODE_FUSED>(p, grid, smem, stream);
     if (nv == 8) return launch_one<PRF, 8, MODE_FUSED>(p, grid, smem, stream);
     if (nv == 16) return launch_one<PRF, 16, MODE_FUSED>(p, grid, smem, stream);
@@ -721,6 +781,10 @@ cudaError_t max_smem_prf(int nv, int mode, int *bytes)
     if (mode == MODE_EXPAND) return max_smem_one<PRF, 4, MODE_EXPAND>(bytes);
     if (mode == MODE_FRONTIER) return max_smem_one<PRF, 4, MODE_FRONTIER>(bytes);
     if (mode == MODE_GROUPED) return max_smem_one<PRF, 4, MODE_GROUPED>(bytes);
+    if (mode == MODE_FUSED_TMA) {
+        if constexpr (PRF == PRF_AES128) return cudaErrorInvalidValue;
+        else return max_smem_one<PRF, 4, MODE_FUSED_TMA>(bytes);
+    }
     if (nv == 4) return max_smem_one<PRF, 4, MODE_FUSED>(bytes);
     if (nv == 8) return max_smem_one<PRF, 8, MODE_FUSED>(bytes);
     if (nv == 16) return max_smem_one<PRF, 16, MODE_FUSED>(bytes);

@@ -103,10 +103,15 @@ struct EvalParams {
     uint32_t off_stack_hi;    /* levels [stack_split, s-1)                              */
     uint32_t off_tab;         /* AES tables: 128 KiB whose shared-window address is a
                                  multiple of 64 KiB                                     */
+    uint32_t off_tile;        /* MODE_FUSED_TMA: per warp, one work item's rows (64 << s bytes),
+                                 then one 8-byte mbarrier per warp at off_tile_bar        */
+    uint32_t off_tile_bar;
 };
 
 /* Kernel modes. */
-enum { MODE_FUSED = 0, MODE_EXPAND = 1, MODE_FRONTIER = 2, MODE_GROUPED = 3 };
+enum { MODE_FUSED = 0, MODE_EXPAND = 1, MODE_FRONTIER = 2, MODE_GROUPED = 3,
+       MODE_FUSED_TMA = 4 /* MODE_FUSED with each work item's table rows staged into shared memory by
+                             cp.async.bulk (16-column tables, non-AES PRFs, whole-warp key groups) */ };
 
 /* Threads per block / minimum blocks per SM of the kernel instantiated for
  * (prf, nv) where nv = uint4 (4 int32 columns) of a table row handled per pass:
