@@ -714,6 +714,27 @@ int b200dpf_gen_batch(const int64_t *alphas, const uint32_t *seeds32, int64_t co
     return B200DPF_OK;
 }
 
+int b200dpf_gen_batch_secure(const int64_t *alphas, const uint8_t *seeds44, int64_t count, int64_t n, int prf,
+                             int nthreads, int32_t *keys_a, int32_t *keys_b)
+{
+    if (!alphas || !seeds44 || !keys_a || !keys_b || count < 0) return fail(B200DPF_EINVAL, "bad gen_batch_secure argument");
+    if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    nthreads = (int)std::min<int64_t>(nthreads, std::max<int64_t>(count, 1));
+    std::vector<int> rcs((size_t)nthreads, 0);
+    auto work = [&](int t) {
+        for (int64_t i = t; i < count; i += nthreads)
+            if (host::gen_secure(alphas[i], n, seeds44 + 44 * i, prf, keys_a + i * host::KEY_WORDS, keys_b + i * host::KEY_WORDS))
+                rcs[(size_t)t] = -1;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    for (int r : rcs)
+        if (r) return fail(B200DPF_EINVAL, "gen_batch_secure: invalid alpha/n/prf in batch");
+    return B200DPF_OK;
+}
+
 int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n)
 {
     if (!key || !out_n) return fail(B200DPF_EINVAL, "null buffer");

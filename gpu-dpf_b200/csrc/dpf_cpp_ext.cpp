@@ -111,6 +111,23 @@ std::vector<at::Tensor> gen_batch(const at::Tensor &alphas, int64_t n, const at:
     return {a, b};
 }
 
+/* batched keygen from the ChaCha20 DRBG: seeds = 44 bytes of entropy per key, concatenated */
+std::vector<at::Tensor> gen_batch_secure(const at::Tensor &alphas, int64_t n, const std::string &seeds, int prf, int nthreads)
+{
+    at::Tensor al = alphas.to(at::kLong).contiguous().cpu();
+    TORCH_CHECK(al.dim() == 1 && (int64_t)seeds.size() == 44 * al.numel(), "gen_batch_secure: need 44 seed bytes per key");
+    const int64_t count = al.numel();
+    at::Tensor a = torch::zeros({count, kKeyWords}, at::kInt);
+    at::Tensor b = torch::zeros({count, kKeyWords}, at::kInt);
+    {
+        py::gil_scoped_release nogil;
+        check(b200dpf_gen_batch_secure(al.data_ptr<int64_t>(), reinterpret_cast<const uint8_t *>(seeds.data()), count, n, prf,
+                                       nthreads, a.data_ptr<int32_t>(), b.data_ptr<int32_t>()),
+              "gen_batch_secure");
+    }
+    return {a, b};
+}
+
 /* dpf_wrapper.cu:70-84 */
 at::Tensor eval_cpu(const at::Tensor &key, int prf)
 {
@@ -382,6 +399,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("key_pack", &key_pack, "compact wire form of a key (bytes)");
     m.def("key_unpack", &key_unpack, "restore an int32[524] key from its compact form");
     m.def("gen_secure", &gen_secure, "dpf gen from a ChaCha20 DRBG (seed: >= 44 bytes)");
+    m.def("gen_batch_secure", &gen_batch_secure, "batched keygen from a ChaCha20 DRBG (44 seed bytes per key)", py::arg("alphas"),
+          py::arg("n"), py::arg("seeds"), py::arg("prf"), py::arg("nthreads") = 0);
     m.def("gen_batch", &gen_batch, "batched multi-threaded keygen", py::arg("alphas"), py::arg("n"), py::arg("seeds"),
           py::arg("prf"), py::arg("nthreads") = 0);
     m.def("eval_init_sharded", &eval_init_sharded, "eval_init for one entry-range shard", py::arg("table"),

@@ -83,10 +83,17 @@ class DPF(object):
         self.prf_method_string = self._PRF_NAMES[self.prf_method]
 
     # ---- client -----------------------------------------------------------
-    def gen(self, k, n, seed=None, secure=False):
+    def gen(self, k, n, seed=None, secure=None):
         """Two keys for the point function at index k over a domain of n (dpf.py:63-74).
-        secure=True draws every random word from a ChaCha20 DRBG keyed by the seed (the
-        reference's generator only consumes 32 bits of it, dpf_wrapper.cu:52)."""
+
+        By default (no seed given) every random word comes from a ChaCha20 DRBG keyed with fresh
+        os.urandom entropy.  The reference seeds std::mt19937 with 32 bits of its seed
+        (dpf_wrapper.cu:52; its own TODO, dpf.py:65), so a server could enumerate the 2^32 possible
+        generator states of a key it holds and recover the index: that generator is kept only
+        for callers that pass an explicit `seed` (deterministic keys, bit-identical to the
+        reference's for the same seed: golden and parity tests) and do not ask for secure=True."""
+        if secure is None:
+            secure = seed is None
         if seed is None:
             seed = os.urandom(128)
         if n & (n - 1) != 0 and not self.allow_non_pow2:
@@ -100,7 +107,9 @@ class DPF(object):
         return dpf_cpp.gen(k, n, seed, self.prf_method)
 
     def gen_batch(self, indices, n, seeds=None, nthreads=0):
-        """Keys for many indices at once: two int32 [B, 524] tensors (multi-threaded keygen)."""
+        """Keys for many indices at once: two int32 [B, 524] tensors (multi-threaded keygen).
+        seeds=None: ChaCha20-DRBG keys from os.urandom entropy (44 bytes per key); explicit integer
+        seeds select the reference's 32-bit mt19937 generator (deterministic, for tests)."""
         if n & (n - 1) != 0:
             raise Exception("Table num entries (%d) must be a power of two" % (n))
         idx = torch.as_tensor(list(indices), dtype=torch.int64)
@@ -108,7 +117,7 @@ class DPF(object):
             raise Exception("k (%d), the selected element, must be less than n (%d), the number of entries in the table"
                             % (int(idx.max()), n))
         if seeds is None:
-            seeds = torch.from_numpy(np.frombuffer(os.urandom(8 * idx.numel()), dtype=np.int64).copy())
+            return dpf_cpp.gen_batch_secure(idx, n, os.urandom(44 * idx.numel()), self.prf_method, nthreads)
         return dpf_cpp.gen_batch(idx, n, torch.as_tensor(seeds, dtype=torch.int64), self.prf_method, nthreads)
 
     # ---- server -----------------------------------------------------------

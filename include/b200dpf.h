@@ -105,6 +105,11 @@ int b200dpf_gen_batch(const int64_t *alphas, const uint32_t *seeds32, int64_t co
                       int64_t n, int prf, int nthreads,
                       int32_t *keys_a, int32_t *keys_b);
 
+/* Batched b200dpf_gen_secure: seeds44 = count x 44 bytes of caller entropy (key || nonce per key). */
+int b200dpf_gen_batch_secure(const int64_t *alphas, const uint8_t *seeds44, int64_t count,
+                             int64_t n, int prf, int nthreads,
+                             int32_t *keys_a, int32_t *keys_b);
+
 /*
  * One server's share vector on the CPU, natural index order: out[i] =
  * (int32) low32(EvaluateFlat(key, i)), i < n (n read from the key).

@@ -131,6 +131,37 @@ def test_python_api_cpu_side():
     dpf.test_cpu_dpf()
 
 
+def test_secure_keygen_is_the_default(oracle):
+    """dpf.DPF.gen / gen_batch without a seed use the ChaCha20 DRBG (full-width correction words); an explicit seed
+    keeps the reference's 32-bit generator so golden/parity keys stay bit-identical."""
+    import os
+    import dpf
+    d = dpf.DPF(prf=dpf.DPF.PRF_CHACHA20)
+    n = 4096
+    k1, k2 = d.gen(77, n)
+    # the reference draws the upper-level cw_1 words as 32-bit values (dpf.h:450): such slots have words 1..3 zero
+
+    def narrow_slots(key):
+        cw1 = key.numpy().reshape(131, 4)[1:1 + 2 * 12]
+        return int(((cw1[:, 0] != 0) & (cw1[:, 1:] == 0).all(axis=1)).sum())
+    assert narrow_slots(k1) == 0
+    v = oracle.eval_full(k1.numpy(), 2).astype(np.uint32) - oracle.eval_full(k2.numpy(), 2).astype(np.uint32)
+    assert v[77] == 1 and np.count_nonzero(v) == 1
+    legacy1, _ = d.gen(77, n, seed=b"\x01\x02\x03\x04" + bytes(124))
+    legacy2, _ = d.gen(77, n, seed=b"\x01\x02\x03\x04" + bytes(124))
+    want, _ = b200dpf.gen(77, n, 0x04030201, 2)
+    assert torch.equal(legacy1, legacy2) and np.array_equal(legacy1.numpy(), want)
+    assert narrow_slots(legacy1) > 0
+    ka, kb = d.gen_batch([1, 2, 4095], n)
+    for i, idx in enumerate([1, 2, 4095]):
+        v = oracle.eval_full(ka[i].numpy(), 2).astype(np.uint32) - oracle.eval_full(kb[i].numpy(), 2).astype(np.uint32)
+        assert v[idx] == 1 and np.count_nonzero(v) == 1
+    assert not torch.equal(ka, d.gen_batch([1, 2, 4095], n)[0])          # fresh entropy every call
+    sa, _ = b200dpf.gen_batch_secure([9, 10], n, bytes(range(88)), 2)
+    one, _ = b200dpf.gen_secure(10, n, bytes(range(44, 88)), 2)
+    assert np.array_equal(sa[1], one)
+
+
 def test_compact_key_format(golden):
     """pack/unpack round-trips every golden key exactly and shrinks it to 32 + 64*depth bytes, every field
     16-byte aligned (the GPU reads this form in place: b200dpf_eval_packed)."""
