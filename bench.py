@@ -29,7 +29,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "gpu-dpf_b200"))
+sys.path.insert(0, ROOT)
+import gpu_dpf_b200  # noqa: E402,F401  (importable alias of gpu-dpf_b200/; makes dpf, b200dpf, dpf_cpp, sharded importable)
 
 PRF_IDS = {"dummy": 0, "salsa20": 1, "chacha20": 2, "aes128": 3}
 KEY_BYTES = 2096
