@@ -21,7 +21,7 @@ SYMBOLS = [
     "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_gen_batch_secure", "b200dpf_eval_cpu",
     "b200dpf_key_packed_size", "b200dpf_key_pack", "b200dpf_key_unpack", "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
     "b200dpf_eval_packed", "b200dpf_eval_gather", "b200dpf_ctx_set_option", "b200dpf_create_multi", "b200dpf_ctx_device_count", "b200dpf_ctx_axis", "b200dpf_ctx_read_timing",
-    "b200dpf_group_create", "b200dpf_group_eval", "b200dpf_group_bins",
+    "b200dpf_group_create", "b200dpf_group_eval", "b200dpf_group_bins", "b200dpf_ctx_last_device_ms",
     "b200dpf_host_staging", "b200dpf_eval_device", "b200dpf_eval_device_acc", "b200dpf_expand_device", "b200dpf_ctx_n", "b200dpf_ctx_entry_size",
     "b200dpf_ctx_device", "b200dpf_ctx_last_launches", "b200dpf_ctx_set_subtree_log2",
 ]
@@ -60,6 +60,8 @@ def load():
     L.b200dpf_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64p, C.c_int, C.c_int, C.c_int]
     L.b200dpf_group_eval.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int64, C.c_int, _i32p]
     L.b200dpf_group_bins.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_last_device_ms.argtypes = [C.c_void_p]
+    L.b200dpf_ctx_last_device_ms.restype = C.c_double
     L.b200dpf_ctx_read_timing.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), C.c_int,
                                           C.POINTER(C.c_int)]
     L.b200dpf_destroy.argtypes = [C.c_void_p]
@@ -234,6 +236,10 @@ class Context:
 
     def set_subtree_log2(self, s):
         _check(lib().b200dpf_ctx_set_subtree_log2(self.handle, s), "b200dpf_ctx_set_subtree_log2")
+
+    @property
+    def last_device_ms(self):
+        return lib().b200dpf_ctx_last_device_ms(self.handle)
 
     @property
     def last_launches(self):

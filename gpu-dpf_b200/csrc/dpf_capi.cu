@@ -147,6 +147,10 @@ struct b200dpf_ctx {
     cudaEvent_t ev_done = nullptr;
     cudaStream_t last_stream = nullptr;
     bool has_last = false;
+    /* device time of the last host-buffer evaluation (first launch .. last launch), for callers that
+     * want the kernel time next to their own wall clock */
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    bool timed = false;
 };
 
 namespace {
@@ -839,6 +843,8 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     CTX_TRY(cudaDeviceGetAttribute(&c->coop_ok, cudaDevAttrCooperativeLaunch, device));
     CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CTX_TRY(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    CTX_TRY(cudaEventCreate(&c->ev_t0));
+    CTX_TRY(cudaEventCreate(&c->ev_t1));
     CTX_TRY(cudaMalloc(&c->d_gridbar, sizeof(uint32_t)));
     /* the environment is consulted here and nowhere else (b200dpf_ctx_set_option changes a
      * live context) */
@@ -955,6 +961,8 @@ int b200dpf_destroy(b200dpf_ctx *c)
         delete c->bins;
     }
     if (c->ev_done) cudaEventDestroy(c->ev_done);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->d_frontier) cudaFree(c->d_frontier);
     if (c->d_leaf_cache) cudaFree(c->d_leaf_cache);
     if (c->h_keys) cudaFreeHost(c->h_keys);
@@ -1029,8 +1037,11 @@ static int eval_host(b200dpf_ctx *c, const void *keys, size_t key_bytes, const K
      * overtake it (run_pipeline orders the kernels, this orders the H2D) */
     if (c->has_last && c->last_stream != c->stream) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_done, 0));
     CUDA_TRY(cudaMemcpyAsync(c->d_keys, src, key_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->ev_t0, c->stream));
     rc = run_pipeline(c, c->d_keys, kl, nkeys, prf, MODE_FUSED, c->d_out, c->stream);
     if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_t1, c->stream));
+    c->timed = true;
     CUDA_TRY(cudaMemcpyAsync(dst, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (dst != out) std::memcpy(out, dst, out_elems * sizeof(int32_t));
@@ -1554,6 +1565,8 @@ int b200dpf_group_create(b200dpf_ctx **out, const int32_t *const *tables, const 
     GRP_TRY(cudaDeviceGetAttribute(&c->coop_ok, cudaDevAttrCooperativeLaunch, device));
     GRP_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     GRP_TRY(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    GRP_TRY(cudaEventCreate(&c->ev_t0));
+    GRP_TRY(cudaEventCreate(&c->ev_t1));
     GRP_TRY(cudaMalloc(&c->d_gridbar, sizeof(uint32_t)));
     GRP_TRY(cudaMemsetAsync(c->d_gridbar, 0, sizeof(uint32_t), c->stream));
     GRP_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
@@ -1610,16 +1623,30 @@ int b200dpf_group_eval(b200dpf_ctx *c, const int32_t *keys, const int32_t *bins,
     for (int g = 0; g < nbins; g++) count[(size_t)g + 1] += count[(size_t)g];
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c->device);
-    int rc = ensure_host_keys(c, nkeys);
+    /* keys travel in the compact layout, one stride for all bins (that of the deepest): a key for a
+     * 2^10-entry bin has 672 live bytes of its 2096 */
+    const KeyLayout kl = compact_layout(c->depth);
+    const size_t stride = (size_t)kl.stride_v * 16u;
+    const size_t key_bytes = (size_t)nkeys * stride;
+    const size_t unit = host::KEY_WORDS * sizeof(int32_t);
+    int rc = ensure_host_keys(c, (int64_t)((key_bytes + unit - 1) / unit));
     if (rc) return rc;
     B->perm.assign((size_t)nkeys, 0);
     {
         std::vector<int64_t> next(count.begin(), count.end() - 1);
-        for (int64_t b = 0; b < nkeys; b++) {
-            const int64_t pos = next[(size_t)bins[b]]++;
-            B->perm[(size_t)pos] = b;
-            std::memcpy(c->h_keys + pos * host::KEY_WORDS, keys + b * host::KEY_WORDS, host::KEY_WORDS * sizeof(int32_t));
-        }
+        for (int64_t b = 0; b < nkeys; b++) B->perm[(size_t)(next[(size_t)bins[b]]++)] = b;
+        uint8_t *stage = reinterpret_cast<uint8_t *>(c->h_keys);
+        auto pack_range = [&](int64_t p0, int64_t p1) {
+            for (int64_t pos = p0; pos < p1; pos++) {
+                const int64_t b = B->perm[(size_t)pos];
+                pack_compact(keys + b * host::KEY_WORDS, stage + (size_t)pos * stride, B->depth[(size_t)bins[b]]);
+            }
+        };
+        const int nthr = (int)std::min<int64_t>(std::min<int64_t>(8, std::max(1u, std::thread::hardware_concurrency())), nkeys / 2048 + 1);
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthr; t++) pool.emplace_back(pack_range, nkeys * t / nthr, nkeys * (t + 1) / nthr);
+        pack_range(0, nkeys / nthr);
+        for (auto &th : pool) th.join();
     }
     /* key groups and their work-item size: big items amortise the root-to-subtree walk every item
      * pays (there is no frontier: bins are small), small items keep every warp busy */
@@ -1672,7 +1699,6 @@ int b200dpf_group_eval(b200dpf_ctx *c, const int32_t *keys, const int32_t *bins,
         }
     }
     const int passes = c->entry_pad / 16;
-    const size_t key_bytes = (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t);
     const size_t out_elems = (size_t)nkeys * c->entry_size;
     rc = ensure_device_io(c, key_bytes, out_elems);
     if (rc) return rc;
@@ -1694,7 +1720,6 @@ int b200dpf_group_eval(b200dpf_ctx *c, const int32_t *keys, const int32_t *bins,
     fill_common(c, L, s_max, nkeys, 5, &p, &smem);
     p.key_groups = (int)ngroups;
     p.keys = reinterpret_cast<const uint4 *>(c->d_keys);
-    const KeyLayout kl = reference_layout();
     p.key_stride_v = kl.stride_v; p.key_root_v = kl.root_v; p.key_compact = kl.compact;
     p.groups = B->d_descs;
     fill_phase(L, s_max, &p.main);
@@ -1707,6 +1732,7 @@ int b200dpf_group_eval(b200dpf_ctx *c, const int32_t *keys, const int32_t *bins,
     p.zero_b = c->d_counters;
     p.zero_b_words = n_counters;
     c->last_launches = 0;
+    CUDA_TRY(cudaEventRecord(c->ev_t0, c->stream));
     for (int pass = 0; pass < passes; pass++) {
         p.col_off_v = (uint32_t)(pass * 4);
         p.col_off = (uint32_t)(pass * 16);
@@ -1726,6 +1752,8 @@ int b200dpf_group_eval(b200dpf_ctx *c, const int32_t *keys, const int32_t *bins,
         c->last_launches++;
         p.fuse_top = 0;
     }
+    CUDA_TRY(cudaEventRecord(c->ev_t1, c->stream));
+    c->timed = true;
     CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, out_elems * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaEventRecord(c->ev_done, c->stream));
     c->last_stream = c->stream;
@@ -1734,6 +1762,20 @@ int b200dpf_group_eval(b200dpf_ctx *c, const int32_t *keys, const int32_t *bins,
     for (int64_t pos = 0; pos < nkeys; pos++)       /* back to the caller's order */
         std::memcpy(out + B->perm[(size_t)pos] * c->entry_size, c->h_out + pos * c->entry_size, sizeof(int32_t) * (size_t)c->entry_size);
     return B200DPF_OK;
+}
+
+double b200dpf_ctx_last_device_ms(b200dpf_ctx *c)
+{
+    if (!c) return -1.0;
+    if (c->multi) c = multi_first(c);
+    if (!c->timed) return -1.0;
+    DeviceGuard guard(c->device);
+    float ms = -1.0f;
+    if (cudaEventSynchronize(c->ev_t1) != cudaSuccess || cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1) != cudaSuccess) {
+        cudaGetLastError();
+        return -1.0;
+    }
+    return (double)ms;
 }
 
 int b200dpf_group_bins(const b200dpf_ctx *c) { return (c && c->bins) ? (int)c->bins->n.size() : 0; }

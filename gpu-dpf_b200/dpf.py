@@ -258,6 +258,14 @@ class DPF(object):
             dpf_cpp.eval_free(self.buffers)
             self.buffers = None
 
+    def __del__(self):
+        # sample.py's server() builds a DPF per call and drops it: release the device table with the object
+        # (the reference never frees unless eval_init is called again, dpf.py:93-94)
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def __repr__(self):
         if self.buffers is None:
             return "DPF(_uninitialized_, prf_method=%s)" % self.prf_method_string

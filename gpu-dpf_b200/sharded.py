@@ -78,6 +78,7 @@ class ShardedDPF(object):
         self.entry_size = None
         self.n = None
         self._symm = None        # (tensor, handle, rank-0 base pointer) for reduce="fused"
+        self._keys_axis_buffers = None
 
     def eval_init(self, table):
         self.n, self.entry_size = table.shape[0], table.shape[1]
@@ -107,18 +108,27 @@ class ShardedDPF(object):
         holding the complete [B, E] result on rank 0 once the stream is synchronised."""
         nkeys = keys_dev.shape[0]
         if self.axis == "keys":
+            # every rank evaluates its slice straight into its row block of one [world*per, E] buffer;
+            # rank 0 gathers the blocks in place (buffers are kept between calls: at small n a step is
+            # ~0.2 ms and fresh allocations would show)
             b, e = key_slice(nkeys, self.rank, self.world)
-            dev = keys_dev.device
-            part = torch.zeros((max(e - b, 0), self.entry_size), dtype=torch.int32, device=dev)
-            if e > b:
-                self._dpf.eval_gpu_device(keys_dev[b:e], part)
             per = (nkeys + self.world - 1) // self.world
-            padded = torch.zeros((per, self.entry_size), dtype=torch.int32, device=dev)
-            padded[:e - b] = part
-            gathered = [torch.empty_like(padded) for _ in range(self.world)] if self.rank == 0 else None
-            dist.gather(padded, gathered, dst=0, group=self.group)
+            dev = keys_dev.device
+            bufs = self._keys_axis_buffers
+            if bufs is None or bufs[0] != (per, dev):
+                mine = torch.zeros((per, self.entry_size), dtype=torch.int32, device=dev)
+                full = torch.empty((self.world * per, self.entry_size), dtype=torch.int32, device=dev) if self.rank == 0 else None
+                chunks = list(full.split(per)) if self.rank == 0 else None
+                bufs = self._keys_axis_buffers = ((per, dev), mine, full, chunks)
+            _, mine, full, chunks = bufs
+            if e > b:
+                self._dpf.eval_gpu_device(keys_dev[b:e], mine[:e - b])
+            dist.gather(mine, chunks, dst=0, group=self.group)
             if self.rank == 0:
-                return torch.cat(gathered)[:nkeys]
+                if out_dev is not None:
+                    out_dev.copy_(full[:nkeys])
+                    return out_dev
+                return full[:nkeys]
             return None
         if self.world > 1 and self.reduce == "fused":
             t, hdl, root_ptr = self._symm_buffer(nkeys)

@@ -277,6 +277,11 @@ int64_t b200dpf_ctx_n(const b200dpf_ctx *ctx);
 int b200dpf_ctx_entry_size(const b200dpf_ctx *ctx);
 int b200dpf_ctx_device(const b200dpf_ctx *ctx);
 
+/* Device time in milliseconds of the kernels of the most recent b200dpf_eval / _eval_packed /
+ * _eval_gather / _group_eval on this context (CUDA events around the launches, copies excluded);
+ * negative if none. */
+double b200dpf_ctx_last_device_ms(b200dpf_ctx *ctx);
+
 /* Kernels launched by the most recent b200dpf_eval / _eval_device / _expand_device
  * call on this context (for benchmark accounting). */
 int b200dpf_ctx_last_launches(const b200dpf_ctx *ctx);

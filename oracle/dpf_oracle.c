@@ -6,7 +6,8 @@
  * FIPS-197 implementation with a computed S-box, key generation is an
  * iterative bottom-up loop instead of the reference's recursion, and the
  * Mersenne twister is restated from its published recurrence.  Equality with
- * the real reference is established by tests/test_oracle_vs_ref.py.
+ * the real reference is established by tests/test_oracle.py (PRFs, keygen incl. the
+ * RNG stream, EvaluateFlat against oracle/_ref/libdpfref.so and tests/golden/golden_v1.npz).
  */
 #include "dpf_oracle.h"
 

@@ -1,0 +1,17 @@
+# round 2, call E (8 GPUs): multi-GPU tests, the default bench line at N=8 (weak + strong + configs 4/5 + parity),
+# one process driving all 8 GPUs, the reference's unmodified benchmark.py on all GPUs.
+mkdir -p gpurun_out
+nvidia-smi -L | wc -l
+( time timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q --durations=5 ) > gpurun_out/r2e_pytest_multi.txt 2>&1; tail -8 gpurun_out/r2e_pytest_multi.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2e_bench_8gpu.json 2> gpurun_out/r2e_bench_8gpu.err
+python - <<'PY'
+import json
+try:
+    d = json.load(open('gpurun_out/r2e_bench_8gpu.json'))
+    print({k: d[k] for k in ('value', 'ms_per_step', 'n_gpus', 'parity_check')}, d['e2e'])
+    for k in ('strong', 'configs', 'sweep'):
+        for e in d.get(k, []): print(k, e)
+except Exception as exc:
+    print('bench 8gpu failed', exc); print(open('gpurun_out/r2e_bench_8gpu.err').read()[-2000:])
+PY
+timeout 600 python tools/gpu_multi_single_process.py 2>&1 | tee gpurun_out/r2e_multi_single_process.txt
