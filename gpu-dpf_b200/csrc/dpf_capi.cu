@@ -430,6 +430,32 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
             if (rc) return rc;
         }
         s_top = std::max(1, std::min(f_rel - spw_log2, std::min(5, LF.s_max)));
+        if (one_launch && K.balance_top) {
+            /* Size of a tree-top item.  The blocks that start at a key group share its 2^(f_rel - s_top)
+             * items; an item is (walk to its subtree root) + 2^s_top - 1 node pairs, all sequential.
+             * Estimate the phase as rounds x steps x step time, where a step costs the larger of the
+             * warps sharing the SM's binding pipe and the latency of one dependent expansion, and take
+             * the best size: few long items when blocks are plentiful (one round, few busy warps),
+             * more short ones when every warp can be given one.  (AES n=2^20 on 8 shards: s_top 6
+             * instead of 5 halves the phase; n=2^14, 16 key groups: 5 stays best.) */
+            const int nw = L.threads / 32;
+            const double blocks_per_group = std::max(1.0, (double)L.grid / (double)key_groups);
+            double best = 1e300;
+            for (int cand = 1; cand <= std::min(f_rel - spw_log2, std::min(7, LF.s_max)); cand++) {
+                const double tickets = (double)((int64_t)1 << (f_rel - cand)) / (double)(1 << spw_log2) *
+                                       std::max(1.0, (double)key_groups / (double)L.grid);
+                const double quota = std::ceil(tickets / blocks_per_group);
+                const double steps = 0.55 * (c->shard_bits + f_rel - cand) + (double)((1 << cand) - 1);
+                const double full_rounds = std::floor(quota / nw), rest = quota - full_rounds * nw;
+                const double busy = 342.0, latency = 1500.0;        /* per node pair: pipe slots, dependent-chain latency */
+                double t = full_rounds * steps * std::max(nw * busy, latency);
+                if (rest > 0) t += steps * std::max(rest * busy, latency);
+                if (t < best) {
+                    best = t;
+                    s_top = cand;
+                }
+            }
+        }
         fill_phase(LF, s_top, &top);
         top.nsub = (uint32_t)1 << (f_rel - s_top);
         top.sub_first = (uint32_t)c->shard_rank << (f_rel - s_top);

@@ -386,17 +386,29 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
         const uint4 rv = root_s[kslot];
         const Seed root = make_seed(rv.x, rv.y, rv.z, rv.w);
 
-        /* tickets are drawn one item ahead, so the atomic's round trip to L2 overlaps the item being
-         * expanded instead of stalling the warp between items (items can be as small as 7 node pairs) */
+        /* Tickets are drawn one draw ahead, so the atomic's round trip to L2 overlaps the items being
+         * expanded instead of stalling the warp between items (items can be as small as 7 node pairs).
+         * A draw takes a CHUNK of consecutive items, sized from what is left: (remaining / 8x the
+         * warps of the grid), between 1 and 8 -- guided self-scheduling.  With one or two key groups
+         * per GPU (strong scaling over 8 GPUs) every warp of the grid hits the same counter, and
+         * same-address atomics serialise in L2: big early chunks cut their number ~5x, single-item
+         * draws at the end keep the tail fine-grained. */
+        const uint32_t grid_warps = gridDim.x * (uint32_t)(THREADS / 32);
+        const bool chunked = quota == 0xffffffffu;          /* the balanced top round counts single tickets */
+        uint32_t chunk = 1;
+        if (chunked) chunk = min(8u, max(1u, g_tickets / (8u * grid_warps)));
         uint32_t t_raw = 0;
         bool draw = taken < quota;
-        if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, 1u);
+        if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, chunk);
         while (draw) {
-            const uint32_t t = __shfl_sync(0xffffffffu, t_raw, 0);
-            if (t >= g_tickets) break;
-            taken++;
+            const uint32_t t0 = __shfl_sync(0xffffffffu, t_raw, 0);
+            if (t0 >= g_tickets) break;
+            const uint32_t t1 = min(t0 + chunk, g_tickets);
+            taken += t1 - t0;
             draw = taken < quota;
-            if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, 1u);
+            if (chunked) chunk = min(8u, max(1u, (g_tickets - t1) / (8u * grid_warps)));
+            if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, chunk);
+          for (uint32_t t = t0; t < t1; t++) {
             const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
             if (ph.frontier_in != nullptr) {
@@ -427,6 +439,7 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
                                                           : nullptr;
                 eval_subtree<PRF, false>(env, r, g_s, 0);
             }
+          }
         }
 
         if (MODE == MODE_FUSED || MODE == MODE_FUSED_TMA || GROUPED) {
