@@ -130,7 +130,6 @@ struct b200dpf_ctx {
         int one_launch = 1;        /* B200DPF_ONE_LAUNCH     whole evaluation as one cooperative launch    */
         int balance_top = 1;       /* B200DPF_BALANCE_TOP    even per-block shares of the tree-top phase    */
         int timing = 0;            /* B200DPF_TIMING         per-block phase time stamps (diagnostics)      */
-        int split_tickets = 1;     /* B200DPF_SPLIT_TICKETS  several ticket counters per key group when groups are few */
         int tma_rows = 0;          /* B200DPF_TMA_ROWS       fused kernel: stage each item's rows with cp.async.bulk
                                                              (16-column tables, Salsa/ChaCha/dummy); measured slower than
                                                              broadcast loads -- profiles/r2_tma_rows_ab.txt -- so off */
@@ -385,13 +384,7 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
     }
 
     const bool one_launch = K.one_launch != 0 && c->coop_ok != 0;
-    /* ticket ranges per key group: at least ~32 counters in play, at least 32 tickets per range */
-    int split_log2 = 0;
-    if (K.split_tickets != 0)
-        while (split_log2 < 5 && (key_groups << split_log2) < 32 &&
-               ((((int64_t)1 << rel) >> spw_log2) >> (split_log2 + 1)) >= 32)
-            split_log2++;
-    const size_t n_main_counters = ((size_t)passes * (size_t)key_groups) << split_log2;
+    const size_t n_main_counters = (size_t)passes * (size_t)key_groups;
     rc = ensure_buffer(reinterpret_cast<void **>(&c->d_counters), &c->counters_cap, n_main_counters * sizeof(uint32_t));
     if (rc) return rc;
     {
@@ -492,7 +485,6 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
         smem = (size_t)p.off_tile + tile_bytes;
     }
     fill_phase(L, s, &p.main);
-    p.main.split_log2 = split_log2;
     p.main.nsub = (uint32_t)1 << rel;
     p.main.sub_first = (uint32_t)c->shard_rank << rel;
     if (f_rel > 0) {
@@ -610,7 +602,7 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
         p.col_off = (uint32_t)(pass * 4 * nv);
         p.ncols = (uint32_t)std::max(0, std::min(4 * nv, c->entry_size - pass * 4 * nv));
         if (p.ncols == 0) break;
-        p.main.counters = c->d_counters + (((size_t)pass * key_groups) << split_log2);
+        p.main.counters = c->d_counters + (size_t)pass * key_groups;
         rc = launch_main(nv, mode_kernel);
         if (rc) return rc;
     }
@@ -893,7 +885,6 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     c->knobs.balance_top = env_int("B200DPF_BALANCE_TOP", c->knobs.balance_top);
     c->knobs.timing = env_int("B200DPF_TIMING", c->knobs.timing);
     c->knobs.tma_rows = env_int("B200DPF_TMA_ROWS", c->knobs.tma_rows);
-    c->knobs.split_tickets = env_int("B200DPF_SPLIT_TICKETS", c->knobs.split_tickets);
     CTX_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
     CTX_TRY(upload_aes_table(host::aes_te0()));
 
@@ -1245,7 +1236,7 @@ int b200dpf_ctx_set_option(b200dpf_ctx *c, const char *name, int value)
         {"frontier_mb", &c->knobs.frontier_mb, 1, 1 << 16}, {"subtree_log2", &c->knobs.subtree_log2, 0, 16},
         {"mac_tma", &c->knobs.mac_tma, 0, 1},             {"one_launch", &c->knobs.one_launch, 0, 1},
         {"balance_top", &c->knobs.balance_top, 0, 1},     {"timing", &c->knobs.timing, 0, 1},
-        {"tma_rows", &c->knobs.tma_rows, 0, 1},           {"split_tickets", &c->knobs.split_tickets, 0, 1},
+        {"tma_rows", &c->knobs.tma_rows, 0, 1},
     };
     for (auto &o : opts)
         if (std::strcmp(o.name, name) == 0) {

@@ -325,19 +325,13 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
 
     constexpr bool GROUPED = (MODE == MODE_GROUPED);
     uint32_t taken = 0;
-    /* the unit blocks move between is a (key group, ticket range) pair: "virtual group" v */
-    const int split = GROUPED ? 0 : ph.split_log2;
-    const int vgroups = p.key_groups << split;
-    int loaded_kg = -1;                  /* key group whose correction words are in shared memory */
-    for (int j = 0; j < vgroups; j++) {
-        const int v = (int)((blockIdx.x + (unsigned)j) % (unsigned)vgroups);
-        const int kg = v >> split;
-        const uint32_t ticket_base = ((uint32_t)v & ((1u << split) - 1u)) * (ntickets >> split);
+    for (int j = 0; j < p.key_groups; j++) {
+        const int kg = (int)((blockIdx.x + (unsigned)j) % (unsigned)p.key_groups);
 
         /* what this key group evaluates: the context's one table, or (grouped) its own bin */
         int g_depth = p.depth, g_s = ph.s, g_walk_first = ph.walk_first_level, g_walk_steps = ph.walk_steps;
         int g_key_first = kg * kpw, g_key_last = p.nkeys - 1;
-        uint32_t g_tickets = ntickets >> split;
+        uint32_t g_tickets = ntickets;
         const uint4 *g_table = p.table;
         if (GROUPED) {
             const GroupDesc g = p.groups[kg];
@@ -352,11 +346,10 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
         }
 
         if (quota != 0xffffffffu && __syncthreads_and(taken >= quota)) break;   /* the block's share is done */
-        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(ph.counters + v) < g_tickets) ? 1 : 0;
+        if (tid == 0) *flag_s = (*reinterpret_cast<volatile uint32_t *>(ph.counters + kg) < g_tickets) ? 1 : 0;
         __syncthreads();
         const bool has_work = (*flag_s != 0);
-        if (has_work && loaded_kg != kg) {
-            loaded_kg = kg;
+        if (has_work) {
             /* correction words of this key group -> shared, [level][bank][bit][key] */
             const int per_key = g_depth * 4;
             for (int i = tid; i < per_key * kpw; i += THREADS) {
@@ -396,17 +389,17 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
         /* Tickets are drawn one draw ahead, so the atomic's round trip to L2 overlaps the items being
          * expanded instead of stalling the warp between items (items can be as small as 7 node pairs).
          * A draw takes a CHUNK of consecutive items, sized from what is left: (remaining / 8x the
-         * warps of the grid), between 1 and 8 -- guided self-scheduling.  With one or two key groups
-         * per GPU (strong scaling over 8 GPUs) every warp of the grid hits the same counter, and
-         * same-address atomics serialise in L2: big early chunks cut their number ~5x, single-item
-         * draws at the end keep the tail fine-grained. */
+         * warps of the grid), between 1 and 8 -- guided self-scheduling: big early chunks when a key
+         * group holds many more items than the grid has warps, single items at the end keep the tail
+         * fine-grained.  (Cutting a group's tickets into several counters was tried for the case of
+         * one or two key groups per GPU and measured slower: profiles/r2_ticket_split_ab.txt.) */
         const uint32_t grid_warps = gridDim.x * (uint32_t)(THREADS / 32);
         const bool chunked = quota == 0xffffffffu;          /* the balanced top round counts single tickets */
         uint32_t chunk = 1;
         if (chunked) chunk = min(8u, max(1u, g_tickets / (8u * grid_warps)));
         uint32_t t_raw = 0;
         bool draw = taken < quota;
-        if (draw && lane == 0) t_raw = atomicAdd(ph.counters + v, chunk);
+        if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, chunk);
         while (draw) {
             const uint32_t t0 = __shfl_sync(0xffffffffu, t_raw, 0);
             if (t0 >= g_tickets) break;
@@ -414,9 +407,9 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
             taken += t1 - t0;
             draw = taken < quota;
             if (chunked) chunk = min(8u, max(1u, (g_tickets - t1) / (8u * grid_warps)));
-            if (draw && lane == 0) t_raw = atomicAdd(ph.counters + v, chunk);
+            if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, chunk);
           for (uint32_t t = t0; t < t1; t++) {
-            const uint32_t q = ((ticket_base + t) << spw_log2) + sslot;   /* this lane's subtree */
+            const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
             if (ph.frontier_in != nullptr) {
                 /* written earlier in this launch (before the grid barrier) or by the previous one:

@@ -22,13 +22,8 @@ struct PhaseParams {
     int level_base;           /* level of the subtree's bottom expansion (0 = leaves)   */
     uint32_t sub_first;       /* breadth-first index of the shard's first 2^s-subtree   */
     uint32_t nsub;            /* number of 2^s-subtrees in this shard                   */
-    uint32_t *counters;       /* [key_groups << split_log2] tickets, zero at phase start; one
-                                 ticket = 32/kpw consecutive subtrees for the group's kpw keys */
-    int split_log2;           /* each key group's ticket range is cut into 2^split_log2 ranges
-                                 with a counter of their own: with one or two key groups per GPU
-                                 every warp of the grid would otherwise draw from the same
-                                 address, and same-address atomics serialise in L2 (measured:
-                                 ~25 ns each, profiles/r2_phase_timing_few_key_groups_*)       */
+    uint32_t *counters;       /* [key_groups] tickets, zero at phase start; one ticket =
+                                 32/kpw consecutive subtrees for the group's kpw keys   */
     int stack_split;          /* pending-sibling stack levels [0, split) live in the lo
                                  region, the rest in the hi region                      */
 };
