@@ -336,6 +336,12 @@ def pipe_roofline(prf_name, dpfs_per_s, n_local, sm_mhz):
             "ops_source": ops.get("source", "profiles/pipe_ops.json")}
 
 
+try:   # DRAM bytes per launch of the evaluation kernel, measured with ncu per configuration (tools/gpu_r2_final.sh)
+    TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+except Exception:
+    TRAFFIC = {}
+
+
 class Harness:
     """torch / process-group state shared by every measurement of one bench.py run."""
 
@@ -529,6 +535,10 @@ def run_ours(args):
                    "e2e": r["e2e"]["value"] if r["e2e"] else None, "launches_per_step": r["launches_per_step"],
                    "frac": (alg / (r["ms_per_step"] / 1e3) / 1e9) / (float(load_peaks().get("hbm_gbs", 6650.0)) * ww),
                    "parity_ok": r["parity_check"]["ok"] if r["parity_check"] else None}
+            shards_e = ww if r["axis"] == "entries" else 1
+            pr = pipe_roofline(prf_name, r["value"] / ww, nn // shards_e, (clocks or {}).get("sm_mhz")) if ee == 16 else None
+            out["pipe_frac"] = pr["frac"] if pr else None
+            out["traffic"] = TRAFFIC.get("%s_n%d_e%d_b%d_%dgpu" % (prf_name, nn, ee, bb, ww), {}).get("dram_bytes_per_launch")
             return out
         try:
             if world == 1:
@@ -575,13 +585,8 @@ def run_ours(args):
         alg_bytes = batch * (n // shards * entry * 4 + KEY_BYTES + 4 * entry)
         launch_ms = m["ms_per_step"]
         achieved = alg_bytes / (launch_ms / 1e3) / 1e9
-        traffic = None
-        try:   # measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum), per launch: tools/gpu_r2_traffic.sh
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            key = "%s_n%d_e%d_b%d_%dgpu" % (args.prf, n, entry, batch, world)
-            traffic = tr.get(key, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+        # measured with ncu (dram__bytes_read.sum + dram__bytes_write.sum), per launch
+        traffic = TRAFFIC.get("%s_n%d_e%d_b%d_%dgpu" % (args.prf, n, entry, batch, world), {}).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_kind,
                     "pipe": pipe_roofline(args.prf, value / world, n // shards, (clocks or {}).get("sm_mhz")),

@@ -245,7 +245,10 @@ struct DevEnv {
  * tables, so one block per SM; accumulators (4*NV registers) decide how many
  * threads fit the register file. */
 template <int PRF, int NV> struct KernelShape { enum { THREADS = (NV <= 8 ? 256 : 384), MIN_BLOCKS = (NV <= 8 ? 2 : 1) }; };
-template <int NV> struct KernelShape<PRF_AES128, NV> { enum { THREADS = (NV <= 8 ? 384 : 256), MIN_BLOCKS = 1 }; };
+#ifndef DPF_AES_THREADS
+#define DPF_AES_THREADS 384      /* 8 warps (256) measured against 12 (384): profiles/r2_aes_block_size_ab.txt */
+#endif
+template <int NV> struct KernelShape<PRF_AES128, NV> { enum { THREADS = (NV <= 8 ? DPF_AES_THREADS : 256), MIN_BLOCKS = 1 }; };
 
 extern __shared__ __align__(16) unsigned char g_dyn_smem[];
 
@@ -808,7 +811,7 @@ cudaError_t max_smem_prf(int nv, int mode, int *bytes)
 
 int eval_threads(int prf, int nv)
 {
-    if (prf == PRF_AES128) return nv <= 8 ? 384 : 256;
+    if (prf == PRF_AES128) return nv <= 8 ? DPF_AES_THREADS : 256;
     return nv <= 8 ? 256 : 384;
 }
 
