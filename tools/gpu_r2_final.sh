@@ -2,11 +2,12 @@
 # ncu full captures, DRAM traffic per sweep config
 mkdir -p gpurun_out
 echo "== compute-sanitizer"; bash tools/gpu_sanitize.sh 2>&1 | tail -12
+python bench.py --entries 16384 --steps 50 --no-cpu-baseline --no-sweep --no-parity --no-e2e > /dev/null 2>&1   # wake the GPU up after the sanitizer runs
 echo "== AES block size A/B (384 vs 256 threads), device-timed bench"
 for var in default aes256; do for cfg in "16384 512" "16384 256" "65536 64" "65536 512" "262144 512" "1048576 512"; do set -- $cfg
   if [ $var = aes256 ]; then export LD_LIBRARY_PATH=$PWD/gpu-dpf_b200/variants/aes256; else unset LD_LIBRARY_PATH; fi
   python bench.py --entries $1 --batch-per-gpu $2 --steps 20 --no-cpu-baseline --no-sweep --no-parity --no-e2e 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$var n=$1 B=$2', round(d['value']), round(d['ms_per_step'],4))"
+import json,sys; d=json.loads(sys.stdin.read()); print('$var n=$1 B=$2', round(d['value']), round(d['ms_per_step'],4), d['clocks']['sm_mhz'], d['clocks']['reasons'])"
 done; done | tee gpurun_out/r2_aes_block_size_ab.txt
 unset LD_LIBRARY_PATH
 echo "== default bench"
@@ -23,8 +24,4 @@ for prf in aes128 salsa20 chacha20; do for n in 65536 262144; do
 done; done
 ncu --metrics $M --clock-control none -k regex:dpf_eval_kernel -s 2 -c 1 --csv --log-file gpurun_out/r2_traffic_aes128_n16384_b256.csv \
     python bench.py --entries 16384 --batch-per-gpu 256 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-parity > /dev/null 2>&1
-echo "== ncu full captures (AES with source; Salsa, ChaCha)"
-ncu --set full --clock-control none --import-source on -k regex:dpf_eval_kernel -s 2 -c 1 -f -o gpurun_out/r2_prof_aes128_n2e20 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-parity > gpurun_out/r2_ncu_aes.log 2>&1
-ncu --set full --clock-control none -k regex:dpf_eval_kernel -s 2 -c 1 -f -o gpurun_out/r2_prof_salsa20_n2e20 python bench.py --prf salsa20 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-parity > gpurun_out/r2_ncu_salsa.log 2>&1
-ncu --set full --clock-control none -k regex:dpf_eval_kernel -s 2 -c 1 -f -o gpurun_out/r2_prof_chacha20_n2e20 python bench.py --prf chacha20 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-sweep --no-parity > gpurun_out/r2_ncu_chacha.log 2>&1
-ls -la gpurun_out/*.ncu-rep gpurun_out/r2_* 2>/dev/null | awk '{print $5, $9}'
+ls -la gpurun_out/r2_* 2>/dev/null | awk '{print $5, $9}'
