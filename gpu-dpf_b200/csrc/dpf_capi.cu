@@ -1074,6 +1074,8 @@ static int eval_host(b200dpf_ctx *c, const void *keys, size_t key_bytes, const K
     return B200DPF_OK;
 }
 
+static int eval_gather_impl(b200dpf_ctx *c, const int32_t *const *keys, int64_t nkeys, int prf, int32_t *out);
+
 int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, int32_t *out)
 {
     int rc = check_eval_args(c, keys, nkeys, prf, out);
@@ -1082,6 +1084,13 @@ int b200dpf_eval(b200dpf_ctx *c, const int32_t *keys, int64_t nkeys, int prf, in
         if (host::key_n(keys + b * host::KEY_WORDS) != c->n)
             return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
                         (long long)host::key_n(keys + b * host::KEY_WORDS), (long long)c->n);
+    if (!is_pinned_host(keys)) {
+        /* pageable keys have to be staged by the CPU anyway: stage only their live 32 + 64*depth bytes
+         * (44 % of a key at n = 2^14, 63 % at 2^20) and let the DMA of a chunk overlap the next one */
+        std::vector<const int32_t *> ptrs((size_t)nkeys);
+        for (int64_t b = 0; b < nkeys; b++) ptrs[(size_t)b] = keys + b * host::KEY_WORDS;
+        return eval_gather_impl(c, ptrs.data(), nkeys, prf, out);
+    }
     if (c->multi) return multi_eval_host(c, keys, host::KEY_WORDS * sizeof(int32_t), reference_layout(), nkeys, prf, out);
     return eval_host(c, keys, (size_t)nkeys * host::KEY_WORDS * sizeof(int32_t), reference_layout(), nkeys, prf, out);
 }
@@ -1102,14 +1111,11 @@ static inline void pack_compact(const int32_t *key, uint8_t *dst, int depth)
     }
 }
 
-int b200dpf_eval_gather(b200dpf_ctx *c, const int32_t *const *keys, int64_t nkeys, int prf, int32_t *out)
+/* keys given as pointers (already validated): gather the live parts into pinned staging in the compact
+ * layout, upload chunk by chunk while gathering, evaluate, copy back */
+static int eval_gather_impl(b200dpf_ctx *c, const int32_t *const *keys, int64_t nkeys, int prf, int32_t *out)
 {
-    int rc = check_eval_args(c, keys, nkeys, prf, out);
-    if (rc) return rc;
-    for (int64_t b = 0; b < nkeys; b++)
-        if (!keys[b] || host::key_n(keys[b]) != c->n)
-            return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
-                        (long long)(keys[b] ? host::key_n(keys[b]) : -1), (long long)c->n);
+    int rc;
     b200dpf_ctx *c0 = c->multi ? multi_first(c) : c;
     DeviceGuard guard(c0->device);
     if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", c0->device);
@@ -1148,6 +1154,17 @@ int b200dpf_eval_gather(b200dpf_ctx *c, const int32_t *const *keys, int64_t nkey
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (dst != out) std::memcpy(out, dst, out_elems * sizeof(int32_t));
     return B200DPF_OK;
+}
+
+int b200dpf_eval_gather(b200dpf_ctx *c, const int32_t *const *keys, int64_t nkeys, int prf, int32_t *out)
+{
+    int rc = check_eval_args(c, keys, nkeys, prf, out);
+    if (rc) return rc;
+    for (int64_t b = 0; b < nkeys; b++)
+        if (!keys[b] || host::key_n(keys[b]) != c->n)
+            return fail(B200DPF_EINVAL, "key %lld was generated for n=%lld, table has n=%lld", (long long)b,
+                        (long long)(keys[b] ? host::key_n(keys[b]) : -1), (long long)c->n);
+    return eval_gather_impl(c, keys, nkeys, prf, out);
 }
 
 int b200dpf_eval_packed(b200dpf_ctx *c, const uint8_t *packed, int64_t nkeys, int prf, int32_t *out)
