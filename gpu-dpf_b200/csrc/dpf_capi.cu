@@ -130,6 +130,7 @@ struct b200dpf_ctx {
         int one_launch = 1;        /* B200DPF_ONE_LAUNCH     whole evaluation as one cooperative launch    */
         int balance_top = 1;       /* B200DPF_BALANCE_TOP    even per-block shares of the tree-top phase    */
         int timing = 0;            /* B200DPF_TIMING         per-block phase time stamps (diagnostics)      */
+        int top_log2 = 0;          /* B200DPF_TOP_LOG2       log2 leaves-of-the-frontier per tree-top item (0 = estimate) */
         int tma_rows = 0;          /* B200DPF_TMA_ROWS       fused kernel: stage each item's rows with cp.async.bulk
                                                              (16-column tables, Salsa/ChaCha/dummy); measured slower than
                                                              broadcast loads -- profiles/r2_tma_rows_ab.txt -- so off */
@@ -430,7 +431,9 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
             if (rc) return rc;
         }
         s_top = std::max(1, std::min(f_rel - spw_log2, std::min(5, LF.s_max)));
-        if (one_launch && K.balance_top) {
+        if (K.top_log2 > 0) {
+            s_top = std::max(1, std::min(K.top_log2, std::min(f_rel - spw_log2, LF.s_max)));
+        } else if (one_launch && K.balance_top) {
             /* Size of a tree-top item.  The blocks that start at a key group share its 2^(f_rel - s_top)
              * items; an item is (walk to its subtree root) + 2^s_top - 1 node pairs, all sequential.
              * Estimate the phase as rounds x steps x step time, where a step costs the larger of the
@@ -884,6 +887,7 @@ int b200dpf_create(b200dpf_ctx **out, const int32_t *table, int64_t n, int entry
     c->knobs.one_launch = env_int("B200DPF_ONE_LAUNCH", c->knobs.one_launch);
     c->knobs.balance_top = env_int("B200DPF_BALANCE_TOP", c->knobs.balance_top);
     c->knobs.timing = env_int("B200DPF_TIMING", c->knobs.timing);
+    c->knobs.top_log2 = env_int("B200DPF_TOP_LOG2", c->knobs.top_log2);
     c->knobs.tma_rows = env_int("B200DPF_TMA_ROWS", c->knobs.tma_rows);
     CTX_TRY(probe_dynamic_smem_base(&c->smem_base, c->stream));
     CTX_TRY(upload_aes_table(host::aes_te0()));
@@ -1142,8 +1146,11 @@ static int eval_gather_impl(b200dpf_ctx *c, const int32_t *const *keys, int64_t 
         CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(c->d_keys) + (size_t)b0 * stride, stage + (size_t)b0 * stride,
                                  (size_t)(b1 - b0) * stride, cudaMemcpyHostToDevice, c->stream));
     }
+    CUDA_TRY(cudaEventRecord(c->ev_t0, c->stream));
     rc = run_pipeline(c, c->d_keys, compact_layout(c->depth), nkeys, prf, MODE_FUSED, c->d_out, c->stream);
     if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(c->ev_t1, c->stream));
+    c->timed = true;
     int32_t *dst = out;
     if (!is_pinned_host(out)) {
         rc = ensure_host_out(c, out_elems);
@@ -1253,7 +1260,7 @@ int b200dpf_ctx_set_option(b200dpf_ctx *c, const char *name, int value)
         {"frontier_mb", &c->knobs.frontier_mb, 1, 1 << 16}, {"subtree_log2", &c->knobs.subtree_log2, 0, 16},
         {"mac_tma", &c->knobs.mac_tma, 0, 1},             {"one_launch", &c->knobs.one_launch, 0, 1},
         {"balance_top", &c->knobs.balance_top, 0, 1},     {"timing", &c->knobs.timing, 0, 1},
-        {"tma_rows", &c->knobs.tma_rows, 0, 1},
+        {"tma_rows", &c->knobs.tma_rows, 0, 1},           {"top_log2", &c->knobs.top_log2, 0, 7},
     };
     for (auto &o : opts)
         if (std::strcmp(o.name, name) == 0) {

@@ -389,8 +389,11 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
         const uint4 rv = root_s[kslot];
         const Seed root = make_seed(rv.x, rv.y, rv.z, rv.w);
 
-        /* Tickets are drawn one draw ahead, so the atomic's round trip to L2 overlaps the items being
-         * expanded instead of stalling the warp between items (items can be as small as 7 node pairs).
+        /* SMALL items (<= 15 node pairs) draw their tickets one draw ahead, so the atomic's round trip
+         * to L2 overlaps the items being expanded instead of stalling the warp between items.  Big items
+         * draw when they are done: holding a ticket for the length of a 127-pair item makes the hand-out
+         * one item less adaptive at the end of a key group (measured: +0.6 % kernel time at n = 2^20,
+         * profiles/r2_kernel_regression_bisect.txt), and the atomic's latency is nothing against it.
          * A draw takes a CHUNK of consecutive items, sized from what is left: (remaining / 8x the
          * warps of the grid), between 1 and 8 -- guided self-scheduling: big early chunks when a key
          * group holds many more items than the grid has warps, single items at the end keep the tail
@@ -398,6 +401,7 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
          * one or two key groups per GPU and measured slower: profiles/r2_ticket_split_ab.txt.) */
         const uint32_t grid_warps = gridDim.x * (uint32_t)(THREADS / 32);
         const bool chunked = quota == 0xffffffffu;          /* the balanced top round counts single tickets */
+        const bool ahead = g_s <= 4;
         uint32_t chunk = 1;
         if (chunked) chunk = min(8u, max(1u, g_tickets / (8u * grid_warps)));
         uint32_t t_raw = 0;
@@ -410,7 +414,7 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
             taken += t1 - t0;
             draw = taken < quota;
             if (chunked) chunk = min(8u, max(1u, (g_tickets - t1) / (8u * grid_warps)));
-            if (draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, chunk);
+            if (ahead && draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, chunk);
           for (uint32_t t = t0; t < t1; t++) {
             const uint32_t q = (t << spw_log2) + sslot;   /* this lane's subtree */
             Seed start = root;
@@ -443,6 +447,7 @@ __device__ __forceinline__ void run_phase(const EvalParams &p, const PhaseParams
                 eval_subtree<PRF, false>(env, r, g_s, 0);
             }
           }
+            if (!ahead && draw && lane == 0) t_raw = atomicAdd(ph.counters + kg, chunk);
         }
 
         if (MODE == MODE_FUSED || MODE == MODE_FUSED_TMA || GROUPED) {

@@ -302,6 +302,7 @@ int b200dpf_ctx_set_subtree_log2(b200dpf_ctx *ctx, int s);
  *   "leaf_cache_mb" (B200DPF_LEAF_CACHE_MB, 16384)  cap; larger batches run in chunks that fit
  *   "mac_tma"       (B200DPF_MAC_TMA, 1)        cp.async.bulk-staged MAC passes
  *   "balance_top"   (B200DPF_BALANCE_TOP, 1)    even per-block shares of the tree-top phase
+ *   "top_log2"      (B200DPF_TOP_LOG2, 0 = estimate)  size of a tree-top item (log2 frontier nodes)
  *   "timing"        (B200DPF_TIMING, 0)         record per-block phase time stamps (diagnostics)
  * Results never depend on them.
  */

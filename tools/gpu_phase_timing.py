@@ -8,11 +8,13 @@ from common import random_table
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 14
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 prf = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+top_log2 = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 table = random_table(n, 16, seed=1)
 ka, _ = b200dpf.gen_batch(np.arange(batch) % n, n, np.arange(batch) + 7, prf)
 kd = torch.from_numpy(ka).cuda()
 out = torch.empty((batch, 16), dtype=torch.int32, device="cuda")
 ctx = b200dpf.Context(table)
+ctx.set_option("top_log2", top_log2)
 stream = torch.cuda.current_stream().cuda_stream
 for balance in (1, 0):
     ctx.set_option("balance_top", balance)
@@ -33,6 +35,7 @@ for balance in (1, 0):
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     us = lambda a: a / 1e3
+    print("top_log2=%d " % top_log2, end="")
     print("n=%d batch=%d prf=%d balance_top=%d: %.4f ms/eval (%d DPFs/s), %d blocks" % (n, batch, prf, balance, ms, batch / ms * 1e3, len(t)))
     print("   start skew            max %.1f us" % us((t[:, 0] - t0).max()))
     print("   tables + clears       median %.1f  max %.1f us" % (us(np.median(t[:, 1] - t[:, 0])), us((t[:, 1] - t[:, 0]).max())))
