@@ -306,6 +306,8 @@ void fill_phase(const SmemLayout &L, int s, PhaseParams *ph)
  * mode_main is MODE_FUSED (out = [nkeys][entry_size] int32) or MODE_EXPAND
  * (out = [nkeys][n] int32 share vectors).
  */
+constexpr int kRetryWithoutCooperativeLaunch = -1000;   /* internal to run_pipeline */
+
 int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl, int64_t nkeys, int prf, int mode_main,
                        void *out_dev, cudaStream_t stream, bool clear_out, bool want_cache)
 {
@@ -542,6 +544,14 @@ int run_pipeline_chunk(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl
         const cudaError_t e = launch_eval(prf, nv_l, mode_l, p, L.grid, smem, stream);
         if (e != cudaSuccess) {
             c->coop_state_dirty = true;
+            if (e == cudaErrorCooperativeLaunchTooLarge && p.fuse_top) {
+                /* this device cannot keep the whole persistent grid resident (a partitioned GPU, say):
+                 * nothing of this evaluation has been enqueued yet, so fall back -- for the life of the
+                 * context -- to the pipeline of separate launches */
+                cudaGetLastError();
+                c->coop_ok = 0;
+                return kRetryWithoutCooperativeLaunch;
+            }
             return fail(B200DPF_ECUDA, "evaluation kernel launch: %s", cudaGetErrorString(e));
         }
         c->last_launches++;
@@ -629,6 +639,8 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl, int6
     if (!wide || per_group > cap) {
         /* not a cached evaluation (or one key group alone overflows the cap: re-expand per 64 columns) */
         rc = run_pipeline_chunk(c, keys_dev, kl, nkeys, prf, mode_main, out_dev, stream, clear_out, false);
+        if (rc == kRetryWithoutCooperativeLaunch)
+            rc = run_pipeline_chunk(c, keys_dev, kl, nkeys, prf, mode_main, out_dev, stream, clear_out, false);
         launches = c->last_launches;
     } else {
         const int64_t groups_per_chunk = (int64_t)std::max<size_t>(1, cap / per_group);
@@ -639,6 +651,8 @@ int run_pipeline(b200dpf_ctx *c, const void *keys_dev, const KeyLayout &kl, int6
             char *op = reinterpret_cast<char *>(out_dev) + (size_t)k0 * c->entry_size * sizeof(int32_t);
             /* a ragged tail below 17 keys would be lane-split, which the cache layout excludes */
             rc = run_pipeline_chunk(c, kp, kl, kn, prf, mode_main, op, stream, clear_out, kn >= 17);
+            if (rc == kRetryWithoutCooperativeLaunch)
+                rc = run_pipeline_chunk(c, kp, kl, kn, prf, mode_main, op, stream, clear_out, kn >= 17);
             launches += c->last_launches;
         }
     }
