@@ -551,6 +551,13 @@ def run_ours(args):
                 r.pop("table")
                 configs.append(entry_of("C2", "aes128", 1 << 14, 16, 256, r))
             else:
+                # the n x PRF matrix at this GPU count: 512 keys per GPU, axis by table size (key split for
+                # small tables, entry shards + reduce above 2^18), every entry parity-checked on rank 0
+                for prf_name in ("aes128", "salsa20", "chacha20"):
+                    for nn in (1 << 14, 1 << 16, 1 << 18):
+                        r = measure(h, prf_name, nn, 16, 512 * world, 10, 3, axis="auto", parity=2)
+                        r.pop("table")
+                        sweep.append(entry_of("n=2^%d" % (nn.bit_length() - 1), prf_name, nn, 16, 512 * world, r))
                 strong = []
                 for nn in (1 << 16, 1 << 20):
                     rs = measure(h, "aes128", nn, 16, 512, 10, 3, axis="auto", parity=2)

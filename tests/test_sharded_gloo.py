@@ -66,6 +66,68 @@ def _worker(rank, world, port, n, prf, ret):
     dist.destroy_process_group()
 
 
+def _worker_keys_axis(rank, world, port, ret):
+    """axis="keys": batch slices, in-place gather into one [world*per, E] buffer on rank 0, buffers reused
+    between calls -- the product's eval_gpu_device code path with the per-rank GPU evaluation replaced by the
+    oracle (CPU tensors over gloo)."""
+    for sub in ("gpu-dpf_b200", "oracle", "tests"):
+        sys.path.insert(0, os.path.join(ROOT, sub))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from common import random_table, seeded_keys
+    from sharded import ShardedDPF, key_slice
+    orc = O.Oracle()
+    n, prf = 512, 1
+    table = random_table(n, 16, seed=9)
+
+    class OracleDPF:
+        def eval_gpu_device(self, keys, out):
+            out.copy_(torch.from_numpy(orc.eval_dot(keys.numpy(), prf, table)))
+            return out
+
+        def close(self):
+            pass
+
+    class KeysAxis(ShardedDPF):
+        def eval_init(self, t):
+            self.n, self.entry_size = t.shape
+            if self.axis == "auto":
+                self.axis = "keys" if self.n <= self.AUTO_KEYS_MAX_N else "entries"
+            self._dpf = OracleDPF()
+            return self
+
+    d = KeysAxis(prf=prf, axis="auto")
+    d.eval_init(torch.from_numpy(table))
+    assert d.axis == "keys"
+    for batch in (70, 70, 5, 64):                    # same size twice: the kept buffers are reused
+        ka, _, _ = seeded_keys(orc.gen, n, batch, prf, seed=batch)
+        got = d.eval_gpu_device(torch.from_numpy(ka))
+        b, e = key_slice(batch, rank, world)
+        assert 0 <= b <= e <= batch
+        if rank == 0:
+            assert np.array_equal(got.numpy(), orc.eval_dot(ka, prf, table)), batch
+        else:
+            assert got is None
+    if rank == 0:
+        ret.put("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_keys_axis_gather_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_keys_axis, args=(r, world, port, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert ret.get(timeout=5) == "ok"
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_reduce_over_gloo(world):
     ctx = mp.get_context("spawn")
