@@ -156,6 +156,8 @@ class DPF(object):
         if self.buffers is None:
             raise Exception("Must call `eval_init` before `eval_gpu`")
         if isinstance(keys, torch.Tensor):
+            if keys.is_cuda:        # keys already on the device: no staging at all
+                return self.eval_gpu_device(keys.contiguous()).cpu()
             return dpf_cpp.eval_gpu_packed(keys.contiguous(), self.buffers, self.prf_method)
         if len(keys) == 0:
             return torch.zeros((0, self.table_effective_entry_size), dtype=torch.int32)
@@ -181,6 +183,9 @@ class DPF(object):
         then be a raw (e.g. peer-mapped) device address."""
         if self.buffers is None:
             raise Exception("Must call `eval_init` before `eval_gpu`")
+        if self.devices:
+            raise Exception("a multi-device DPF takes host keys (eval_gpu); device-resident evaluation is per GPU "
+                            "(DPF(device=d, shard=(rank, count)) or sharded.ShardedDPF)")
         if not (keys_dev.is_cuda and keys_dev.dtype == torch.int32 and keys_dev.is_contiguous() and keys_dev.dim() == 2
                 and keys_dev.shape[1] == 524 and keys_dev.device.index == self.device):
             raise Exception("keys_dev must be a contiguous int32 [B, 524] tensor on cuda:%d" % self.device)
