@@ -478,7 +478,14 @@ def measure(h, prf_name, n, entry, batch, steps, warmup, world=None, axis="entri
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     dev_ms = h.max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends)), world)
-    res = {"value": batch * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps, "launches_per_step": launches_per_step,
+    # per-step times (max over ranks, step by step): the median is what the sub-millisecond extras report
+    # next to the mean -- one NCCL or driver hiccup in ten 0.3 ms steps moves the mean by a third
+    per_step = torch.tensor([s.elapsed_time(e) for s, e in zip(starts, ends)], dtype=torch.float64, device=h.dev)
+    if world > 1:
+        h.dist.all_reduce(per_step, op=h.dist.ReduceOp.MAX)
+    ms_median = float(per_step.median().item())
+    res = {"value": batch * steps / (dev_ms / 1e3), "ms_per_step": dev_ms / steps, "ms_per_step_median": ms_median,
+           "launches_per_step": launches_per_step,
            "warmup_effective": nwarm + extra_n, "wall_s_timed_region": t_wall, "clocks": clocks, "axis": axis_used,
            "batch": batch, "e2e": None, "parity_check": None}
 
@@ -532,6 +539,7 @@ def run_ours(args):
             alg = bb * (nn * ee * 4 // (ww if r["axis"] == "entries" else 1) // 1 + KEY_BYTES + 4 * ee)
             out = {"config": tag, "prf": prf_name.upper(), "n": nn, "entry_size": ee, "batch": bb, "n_gpus": ww,
                    "axis": r["axis"], "value": r["value"], "ms_per_step": r["ms_per_step"],
+                   "ms_per_step_median": r["ms_per_step_median"],
                    "e2e": r["e2e"]["value"] if r["e2e"] else None, "launches_per_step": r["launches_per_step"],
                    "frac": (alg / (r["ms_per_step"] / 1e3) / 1e9) / (float(load_peaks().get("hbm_gbs", 6650.0)) * ww),
                    "parity_ok": r["parity_check"]["ok"] if r["parity_check"] else None}
@@ -560,17 +568,20 @@ def run_ours(args):
                         sweep.append(entry_of("n=2^%d" % (nn.bit_length() - 1), prf_name, nn, 16, 512 * world, r))
                 strong = []
                 for nn in (1 << 16, 1 << 20):
-                    rs = measure(h, "aes128", nn, 16, 512, 10, 3, axis="auto", parity=2)
+                    rs = measure(h, "aes128", nn, 16, 512, 30 if nn <= (1 << 16) else 10, 3, axis="auto", parity=2)
                     rs.pop("table")
                     one = None
                     if rank == 0:          # the same batch on ONE of these GPUs, this rank alone
-                        one = measure(h, "aes128", nn, 16, 512, 10, 3, world=1, e2e=False, parity=0)
+                        one = measure(h, "aes128", nn, 16, 512, 30 if nn <= (1 << 16) else 10, 3, world=1, e2e=False, parity=0)
                         one.pop("table")
                     h.barrier()
                     if rank == 0:
                         strong.append({"n": nn, "prf": "AES128", "batch": 512, "axis": rs["axis"], "ms_per_step": rs["ms_per_step"],
+                                       "ms_per_step_median": rs["ms_per_step_median"],
                                        "value": rs["value"], "ms_per_step_1gpu": one["ms_per_step"],
+                                       "ms_per_step_1gpu_median": one["ms_per_step_median"],
                                        "speedup_vs_1gpu": one["ms_per_step"] / rs["ms_per_step"],
+                                       "speedup_vs_1gpu_median": one["ms_per_step_median"] / rs["ms_per_step_median"],
                                        "parity_ok": rs["parity_check"]["ok"] if rs["parity_check"] else None})
                 if world == 8 and not args.strong:
                     r = measure(h, "salsa20", 1 << 24, 16, 4096, 2, 3, e2e=False, parity=2)      # config 4
