@@ -18,7 +18,7 @@ PRF_NAMES = {0: "DUMMY", 1: "SALSA20", 2: "CHACHA20", 3: "AES128"}
 
 # every symbol include/b200dpf.h declares
 SYMBOLS = [
-    "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_gen_batch_secure", "b200dpf_eval_cpu",
+    "b200dpf_version", "b200dpf_last_error", "b200dpf_gen", "b200dpf_gen_secure", "b200dpf_gen_batch", "b200dpf_gen_batch_secure", "b200dpf_gen_batch_gpu", "b200dpf_eval_cpu",
     "b200dpf_key_packed_size", "b200dpf_key_pack", "b200dpf_key_unpack", "b200dpf_key_n", "b200dpf_key_depth", "b200dpf_create", "b200dpf_destroy", "b200dpf_eval",
     "b200dpf_eval_packed", "b200dpf_eval_gather", "b200dpf_ctx_set_option", "b200dpf_create_multi", "b200dpf_ctx_device_count", "b200dpf_ctx_axis", "b200dpf_ctx_read_timing",
     "b200dpf_group_create", "b200dpf_group_eval", "b200dpf_group_bins", "b200dpf_ctx_last_device_ms",
@@ -45,6 +45,7 @@ def load():
     L.b200dpf_gen_secure.argtypes = [C.c_int64, C.c_int64, C.c_char_p, C.c_size_t, C.c_int, _i32p, _i32p]
     L.b200dpf_gen_batch.argtypes = [_i64p, _u32p, C.c_int64, C.c_int64, C.c_int, C.c_int, _i32p, _i32p]
     L.b200dpf_gen_batch_secure.argtypes = [_i64p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, _i32p, _i32p]
+    L.b200dpf_gen_batch_gpu.argtypes = [_i64p, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.b200dpf_eval_cpu.argtypes = [_i32p, C.c_int, _i32p]
     L.b200dpf_key_packed_size.argtypes = [C.c_int]
     L.b200dpf_key_packed_size.restype = C.c_size_t
@@ -128,6 +129,22 @@ def gen_batch_secure(alphas, n, seed_bytes, prf, nthreads=0):
     a = np.zeros((len(alphas), KEY_WORDS), np.int32)
     b = np.zeros((len(alphas), KEY_WORDS), np.int32)
     _check(lib().b200dpf_gen_batch_secure(alphas, bytes(seed_bytes), len(alphas), n, prf, nthreads, a, b), "b200dpf_gen_batch_secure")
+    return a, b
+
+
+def gen_batch_gpu(alphas, n, seed_bytes, prf, device=0, out_ptrs=None):
+    """GPU keygen; same keys as gen_batch_secure for the same seeds.  out_ptrs=(ptr_a, ptr_b): device
+    addresses to leave the keys at (int32 [count, 524] each) instead of returning host arrays."""
+    alphas = np.ascontiguousarray(alphas, np.int64)
+    assert len(seed_bytes) == 44 * len(alphas)
+    if out_ptrs is not None:
+        _check(lib().b200dpf_gen_batch_gpu(alphas, bytes(seed_bytes), len(alphas), n, prf, device,
+                                           C.c_void_p(out_ptrs[0]), C.c_void_p(out_ptrs[1])), "b200dpf_gen_batch_gpu")
+        return None
+    a = np.zeros((len(alphas), KEY_WORDS), np.int32)
+    b = np.zeros((len(alphas), KEY_WORDS), np.int32)
+    _check(lib().b200dpf_gen_batch_gpu(alphas, bytes(seed_bytes), len(alphas), n, prf, device,
+                                       a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)), "b200dpf_gen_batch_gpu")
     return a, b
 
 

@@ -21,7 +21,7 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB = os.path.join(HERE, "libb200dpf.so")
 EXT = os.path.join(HERE, "dpf_cpp" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
 
-LIB_SOURCES = ["dpf_kernels.cu", "dpf_capi.cu", "dpf_host.cpp"]
+LIB_SOURCES = ["dpf_kernels.cu", "dpf_capi.cu", "dpf_keygen.cu", "dpf_host.cpp"]
 LIB_DEPS = LIB_SOURCES + ["dpf_core.cuh", "dpf_kernels.cuh", "dpf_host.h", os.path.join(INCLUDE, "b200dpf.h")]
 EXT_SOURCES = ["dpf_cpp_ext.cpp"]
 

@@ -782,6 +782,46 @@ int b200dpf_gen_batch_secure(const int64_t *alphas, const uint8_t *seeds44, int6
     return B200DPF_OK;
 }
 
+int b200dpf_gen_batch_gpu(const int64_t *alphas, const uint8_t *seeds44, int64_t count, int64_t n, int prf, int device,
+                          int32_t *keys_a, int32_t *keys_b)
+{
+    if (!alphas || !seeds44 || !keys_a || !keys_b || count < 0) return fail(B200DPF_EINVAL, "bad gen_batch_gpu argument");
+    if (n < 2 || n > ((int64_t)1 << 32) || (n & (n - 1)) != 0) return fail(B200DPF_EINVAL, "n=%lld must be a power of two in [2, 2^32]", (long long)n);
+    if (prf < B200DPF_PRF_DUMMY || prf > B200DPF_PRF_AES128) return fail(B200DPF_EINVAL, "unknown prf id %d", prf);
+    for (int64_t i = 0; i < count; i++)
+        if (alphas[i] < 0 || alphas[i] >= n) return fail(B200DPF_EINVAL, "gen_batch_gpu: alpha[%lld]=%lld out of range", (long long)i, (long long)alphas[i]);
+    if (count == 0) return B200DPF_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(B200DPF_ECUDA, "no CUDA device available (use b200dpf_gen_batch_secure on the CPU)");
+    if (device < 0 || device >= ndev) return fail(B200DPF_EINVAL, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(B200DPF_ECUDA, "cudaSetDevice(%d) failed", device);
+    const size_t key_bytes = (size_t)count * host::KEY_WORDS * sizeof(int32_t);
+    int64_t *d_alphas = nullptr;
+    uint8_t *d_seeds = nullptr;
+    uint32_t *d_te0 = nullptr;
+    uint4 *d_a = nullptr, *d_b = nullptr;
+    cudaError_t e = cudaMalloc(&d_alphas, (size_t)count * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_seeds, (size_t)count * 44);
+    if (e == cudaSuccess) e = cudaMalloc(&d_te0, 256 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_a, key_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_b, key_bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(d_alphas, alphas, (size_t)count * sizeof(int64_t), cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(d_seeds, seeds44, (size_t)count * 44, cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(d_te0, host::aes_te0(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_keygen(prf, d_alphas, d_seeds, count, ilog2(n), (uint64_t)n, d_te0, d_a, d_b, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(keys_a, d_a, key_bytes, cudaMemcpyDefault);      /* host or device destination */
+    if (e == cudaSuccess) e = cudaMemcpy(keys_b, d_b, key_bytes, cudaMemcpyDefault);
+    cudaFree(d_alphas);
+    cudaFree(d_seeds);
+    cudaFree(d_te0);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    if (e != cudaSuccess) return fail(B200DPF_ECUDA, "gen_batch_gpu: %s", cudaGetErrorString(e));
+    return B200DPF_OK;
+}
+
 int b200dpf_eval_cpu(const int32_t *key, int prf, int32_t *out_n)
 {
     if (!key || !out_n) return fail(B200DPF_EINVAL, "null buffer");

@@ -159,6 +159,11 @@ struct PeerParts {
 };
 cudaError_t launch_sum_partials(uint32_t *dst, const PeerParts &parts, size_t words, cudaStream_t stream);
 
+/* Batched key generation on the device (dpf_keygen.cu): one thread per key pair, ChaCha20-DRBG draws
+ * from 44 seed bytes per key; keys in the reference wire format, [count][131] 128-bit slots each. */
+cudaError_t launch_keygen(int prf, const int64_t *alphas, const uint8_t *seeds44, int64_t count, int depth, uint64_t n,
+                          const uint32_t *te0, uint4 *keys_a, uint4 *keys_b, cudaStream_t stream);
+
 /* Maximum dynamic shared memory the evaluation kernel may be given. */
 cudaError_t eval_max_smem(int prf, int nv, int mode, int *bytes);
 

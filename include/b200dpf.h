@@ -111,6 +111,16 @@ int b200dpf_gen_batch_secure(const int64_t *alphas, const uint8_t *seeds44, int6
                              int32_t *keys_a, int32_t *keys_b);
 
 /*
+ * The same batched keygen on a GPU (one thread per key pair; SURVEY.md section 8(f) rank 1, "optionally
+ * GPU"): bit-identical to b200dpf_gen_batch_secure for identical seeds.  alphas and seeds44 are host
+ * arrays; keys_a / keys_b may be host or device memory ([count][524] int32), so a load generator can
+ * leave the keys on the device and hand them to b200dpf_eval_device.  Key generation is the CLIENT's
+ * step of the protocol; this entry point exists for benchmarks and load generators.
+ */
+int b200dpf_gen_batch_gpu(const int64_t *alphas, const uint8_t *seeds44, int64_t count, int64_t n, int prf,
+                          int device, int32_t *keys_a, int32_t *keys_b);
+
+/*
  * One server's share vector on the CPU, natural index order: out[i] =
  * (int32) low32(EvaluateFlat(key, i)), i < n (n read from the key).
  * Replaces: dpf_cpp.eval_cpu -> eval_dpf_cpu()            dpf_wrapper.cu:70-84.
