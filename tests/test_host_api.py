@@ -222,3 +222,26 @@ def test_reference_dpf_py_runs_on_our_extension():
     spec.loader.exec_module(mod)
     mod.test_cpu_dpf_one_hot()
     assert repr(mod.DPF()) == "DPF(_uninitialized_, prf_method=AES128)"
+
+
+def test_gpu_entry_points_fail_loudly_without_a_gpu():
+    """No CUDA device in this container: every GPU entry point returns B200DPF_ECUDA with a message that says
+    so -- there is no CPU evaluation behind the product API."""
+    import ctypes as C
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    L = b200dpf.lib()
+    table = np.arange(256 * 16, dtype=np.int32).reshape(256, 16)
+    h = C.c_void_p()
+    ptr = table.ctypes.data_as(C.c_void_p)
+    assert L.b200dpf_create(C.byref(h), ptr, 256, 16, 0, 0, 1) == -2 and b"no CUDA device" in L.b200dpf_last_error()
+    devs = (C.c_int * 2)(0, 1)
+    assert L.b200dpf_create_multi(C.byref(h), ptr, 256, 16, devs, 2, 0) == -2 and b"no CUDA device" in L.b200dpf_last_error()
+    tabs = (C.c_void_p * 1)(table.ctypes.data)
+    sizes = np.array([256], np.int64)
+    assert L.b200dpf_group_create(C.byref(h), tabs, sizes, 1, 16, 0) == -2 and b"no CUDA device" in L.b200dpf_last_error()
+    with pytest.raises(b200dpf.B200DPFError, match="no CUDA device"):
+        b200dpf.gen_batch_gpu([1, 2], 256, bytes(88), 3)
+    a, b = b200dpf.gen_batch_secure([1, 2], 256, bytes(88), 3)          # the CPU keygen is its own API, not a fallback
+    assert a.shape == (2, 524)
