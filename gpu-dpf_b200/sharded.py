@@ -115,15 +115,22 @@ class ShardedDPF(object):
             per = (nkeys + self.world - 1) // self.world
             dev = keys_dev.device
             bufs = self._keys_axis_buffers
+            # NCCL: one all-gather kernel (a gather is a batch of point-to-point sends with twice the latency;
+            # the [B, E] result is a few KiB, so every rank receiving it costs nothing); gloo: a plain gather
+            use_all_gather = dist.get_backend(self.group) == "nccl"
             if bufs is None or bufs[0] != (per, dev):
                 mine = torch.zeros((per, self.entry_size), dtype=torch.int32, device=dev)
-                full = torch.empty((self.world * per, self.entry_size), dtype=torch.int32, device=dev) if self.rank == 0 else None
+                need_full = self.rank == 0 or use_all_gather
+                full = torch.empty((self.world * per, self.entry_size), dtype=torch.int32, device=dev) if need_full else None
                 chunks = list(full.split(per)) if self.rank == 0 else None
                 bufs = self._keys_axis_buffers = ((per, dev), mine, full, chunks)
             _, mine, full, chunks = bufs
             if e > b:
                 self._dpf.eval_gpu_device(keys_dev[b:e], mine[:e - b])
-            dist.gather(mine, chunks, dst=0, group=self.group)
+            if use_all_gather:
+                dist.all_gather_into_tensor(full, mine, group=self.group)
+            else:
+                dist.gather(mine, chunks, dst=0, group=self.group)
             if self.rank == 0:
                 if out_dev is not None:
                     out_dev.copy_(full[:nkeys])
