@@ -637,7 +637,7 @@ def run_ours(args):
                        "n": n, "entry_size": entry, "prf": args.prf.upper(), "global_batch": batch,
                        "parallelism": ("%s x%d + %s" % ("entry-shard" if m["axis"] == "entries" else "key-split", world,
                                        ("NCCL reduce" if args.reduce == "nccl" else "in-kernel peer-memory red.add (symmetric memory)")
-                                       if m["axis"] == "entries" else "NCCL gather")) if world > 1 else "single GPU",
+                                       if m["axis"] == "entries" else "NCCL all-gather")) if world > 1 else "single GPU",
                        "l2": "256 MiB device buffer zeroed before every timed step (L2 flush); table %d MiB" % (n * entry * 4 >> 20),
                        "vs_baseline_ref": "reference README V100 number (BASELINE.md)" if published else None},
             "e2e": m["e2e"], "gpu_launches": m["launches_per_step"] * args.steps, "roofline": roofline,
