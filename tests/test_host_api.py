@@ -245,3 +245,29 @@ def test_gpu_entry_points_fail_loudly_without_a_gpu():
         b200dpf.gen_batch_gpu([1, 2], 256, bytes(88), 3)
     a, b = b200dpf.gen_batch_secure([1, 2], 256, bytes(88), 3)          # the CPU keygen is its own API, not a fallback
     assert a.shape == (2, 524)
+
+
+def test_sharded_key_validation_without_a_gpu():
+    """ShardedDPF refuses keys made for another table size before anything reaches a GPU (the device-resident
+    path takes the tree depth from the context, so a wrong key would otherwise evaluate to garbage)."""
+    from sharded import ShardedDPF, key_slice
+    d = ShardedDPF(prf=2)
+    d.n, d.entry_size = 1024, 16
+    good, _ = b200dpf.gen(5, 1024, 1, 2)
+    wrong, _ = b200dpf.gen(5, 2048, 1, 2)
+    d._check_keys(torch.from_numpy(np.stack([good, good])))
+    with pytest.raises(RuntimeError, match="different table size"):
+        d._check_keys(torch.from_numpy(np.stack([good, wrong])))
+    with pytest.raises(Exception, match=r"int32 \[B, 524\]"):
+        d._check_keys(torch.zeros((2, 100), dtype=torch.int32))
+    assert [key_slice(70, r, 3) for r in range(3)] == [(0, 24), (24, 48), (48, 70)]
+
+
+def test_binned_dpf_argument_checks_without_a_gpu():
+    import dpf
+    d = dpf.BinnedDPF(prf=dpf.DPF.PRF_SALSA20)
+    with pytest.raises(Exception, match="power of two"):
+        d.eval_init([torch.zeros((100, 16), dtype=torch.int32)])
+    with pytest.raises(Exception, match="eval_init"):
+        d.eval_gpu([], [])
+    assert "uninitialized" in repr(d)
